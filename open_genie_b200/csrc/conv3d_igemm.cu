@@ -1,0 +1,443 @@
+// conv3d_igemm.cu — stride-1 3-D convolution forward and data-gradient as an implicit GEMM on the
+// 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA.
+//
+//   D[m][n] = sum_k A[m][k] * B[n][k]      m = output voxel (n,t,h,w), n = output channel,
+//                                           k = (segment, tap, input channel)
+//
+// A is never materialised: one k-block = 64 channels of ONE filter tap, and the 128 voxels of an M tile
+// form a (bw x bh x bt) box of the NDHWC activation tensor, so the A tile of tap (it,ih,iw) is the SAME
+// box shifted by (it-pt, ih-ph, iw-pw) — a single 5-D TMA tile load whose out-of-bounds elements are
+// zero-filled by the hardware. That zero fill *is* the convolution padding, including the causal
+// (front-only) time padding of CausalConv3d: pt = kt-1 simply shifts the box start to negative t.
+// The reference does this with an explicit F.pad copy followed by conv3d (genie/module/video.py:160-192).
+//
+// Forward uses K-major weights w[cout][k]; the data gradient reuses the SAME weight buffer as an
+// MN-major B operand (k = cout rows of 64, n = cin contiguous) with mirrored taps, so no transposed
+// weight copy ever exists.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0    TMA producer (one elected lane)
+//   warp 1    TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5 epilogue: TMEM -> registers -> (+bias) -> global, double-buffered against the next tile's MMAs
+#include "og_host.cuh"
+#include "og_ptx.cuh"
+
+namespace og {
+extern std::atomic<uint64_t> g_launches;
+
+struct IgemmSeg {
+  int cin_blocks;  // channels / 64
+  int kt, kh, kw;
+  int pt, ph, pw;
+};
+
+struct IgemmParams {
+  int nseg;
+  IgemmSeg seg[2];
+  int sgn;         // +1: forward (x[v + tap - pad]); -1: data gradient (dy[v - (tap - pad)])
+  int b_mn_major;  // 0: B tile is [n rows][64 k] (K-major); 1: B tile is [k rows][n] in 64-wide panels (MN-major)
+  int block_n;     // UMMA N (16..256)
+  int num_n_tiles, num_m_tiles;
+  int bw_log2, bh_log2, bt_log2;  // M tile = 2^bw x 2^bh x 2^bt voxels (product 128)
+  int tiles_w, tiles_h, tiles_t;  // M tiles per sample along each axis
+  int T, H, W;
+  int n_out;      // valid output channels
+  long long ldo;  // output row stride in elements
+  void* out;
+  int out_f32;
+  int vec_ok;  // rows are 16-byte aligned and n_out is a multiple of the vector width
+  const float* bias0;
+  const float* bias1;
+  int num_stages;
+  int num_kb;  // k-blocks per tile
+};
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;                       // 64 bf16 = one 128-byte swizzle row
+static constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KiB
+static constexpr int kTmemCols = 512;
+static constexpr int kAccStride = 256;                   // columns between the two accumulator buffers
+static constexpr int kMaxStages = 8;
+static constexpr int kThreads = 192;
+
+struct TileCoord {
+  int n, t0, h0, w0;
+};
+
+__device__ __forceinline__ TileCoord decode_m_tile(const IgemmParams& p, int m_tile) {
+  TileCoord c;
+  int per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
+  c.n = m_tile / per_sample;
+  int r = m_tile - c.n * per_sample;
+  int tw = r % p.tiles_w;
+  r /= p.tiles_w;
+  int th = r % p.tiles_h;
+  int tt = r / p.tiles_h;
+  c.w0 = tw << p.bw_log2;
+  c.h0 = th << p.bh_log2;
+  c.t0 = tt << p.bt_log2;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    og_conv_igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                         const __grid_constant__ CUtensorMap mapB, const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: required by the 128-byte swizzle pattern shared by TMA and the UMMA descriptors
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.block_n * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (p.nseg > 1) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const TileCoord tc = decode_m_tile(p, m_tile);
+        int kb = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const IgemmSeg sg = p.seg[s];
+          const CUtensorMap* mapA = (s == 0) ? &mapA0 : &mapA1;
+          int tap = 0;
+          for (int it = 0; it < sg.kt; ++it)
+            for (int ih = 0; ih < sg.kh; ++ih)
+              for (int iw = 0; iw < sg.kw; ++iw, ++tap) {
+                const int ct = tc.t0 + p.sgn * (it - sg.pt);
+                const int ch = tc.h0 + p.sgn * (ih - sg.ph);
+                const int cw = tc.w0 + p.sgn * (iw - sg.pw);
+                for (int cb = 0; cb < sg.cin_blocks; ++cb, ++kb) {
+                  mbar_wait(&empty[stage], phase ^ 1);
+                  uint8_t* sa = smem + stage * stage_bytes;
+                  uint8_t* sb = sa + kABytes;
+                  mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                  tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, cw, ch, ct, tc.n);
+                  if (!p.b_mn_major) {
+                    tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
+                  } else {
+                    // w[co][tap][ci] as (ci, tap, co): one (64 ci, 1 tap, 64 co) box per 64-wide N panel
+                    for (int pp = 0; pp < p.block_n / 64; ++pp)
+                      tma_load_3d(sb + pp * (64 * 128), &mapB, &full[stage], n_tile * p.block_n + pp * 64, tap,
+                                  cb * kBlockK);
+                  }
+                  if (++stage == p.num_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                  }
+                }
+              }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0u, (uint32_t)p.b_mn_major);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // A: K-major, 128-byte rows, 8-row groups 1024 B apart; advance 16 elements = 32 B inside the row
+            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t bdesc;
+            if (!p.b_mn_major) {
+              bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            } else {
+              // B: MN-major panels [block_n/64][64 k-rows][128 B]; 16 k-rows = 2048 B; panel stride 8192 B
+              bdesc = umma_smem_desc_sw128(b_addr + k * 2048, 64 * 128, 1024);
+            }
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const TileCoord tc = decode_m_tile(p, m_tile);
+      const int dw = row & ((1 << p.bw_log2) - 1);
+      const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
+      const int dt = row >> (p.bw_log2 + p.bh_log2);
+      const long long vox = (((long long)tc.n * p.T + (tc.t0 + dt)) * p.H + (tc.h0 + dh)) * p.W + (tc.w0 + dw);
+      const int col0 = n_tile * p.block_n;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t v[32];
+        if (p.block_n >= 32) {
+          tmem_ld_32x32(t_addr + c, v);
+        } else {
+          uint32_t v16[16];
+          tmem_ld_32x16(t_addr + c, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v16[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0;
+        }
+        tmem_ld_wait();
+        const int cbase = col0 + c;
+        if (cbase >= p.n_out) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float b = 0.f;
+          const int col = cbase + j;
+          if (col < p.n_out) {
+            if (p.bias0) b += __ldg(p.bias0 + col);
+            if (p.bias1) b += __ldg(p.bias1 + col);
+          }
+          f[j] = __uint_as_float(v[j]) + b;
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + vox * p.ldo + cbase;
+          if (p.vec_ok && cbase + 32 <= p.n_out) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.n_out) o[j] = f[j];
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.ldo + cbase;
+          if (p.vec_ok && cbase + 32 <= p.n_out) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(f[j], f[j + 1]);
+              u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              u.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.n_out) o[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int pick_block_n(int n_out, int num_m_tiles, bool mn_major) {
+  // largest N tile that still yields >= one wave of tiles; never below 64 for MN-major B (64-wide panels)
+  const int sms = num_sms();
+  int cap = 16;
+  while (cap < n_out && cap < 256) cap *= 2;
+  const int floor_n = mn_major ? 64 : 16;
+  if (cap < floor_n) cap = floor_n;
+  int bn = cap;
+  while (bn > floor_n && bn > 64) {
+    long long tiles = (long long)num_m_tiles * ((n_out + bn - 1) / bn);
+    if (tiles >= sms) break;
+    bn /= 2;
+  }
+  return bn;
+}
+
+static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const IgemmSeg* segs, int nseg, int sgn,
+                        const void* w, int ldw, int k_off, int b_mn_major, int b_rows /*K rows for MN-major*/,
+                        int b_ntaps, const float* bias0, const float* bias1, void* out, int out_f32, int N, int T,
+                        int H, int W, int n_out, cudaStream_t stream) {
+  OG_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0 && n_out > 0, "conv3d: empty problem");
+  int bw, bh, bt;
+  if (!choose_voxel_box(kBlockM, T, H, W, &bw, &bh, &bt)) {
+    set_error("conv3d: cannot tile T=%d H=%d W=%d into 128-voxel boxes (need power-of-two factors)", T, H, W);
+    return OG_ERR_UNSUPPORTED_SHAPE;
+  }
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = nseg;
+  p.num_kb = 0;
+  for (int s = 0; s < nseg; ++s) {
+    p.seg[s] = segs[s];
+    p.num_kb += segs[s].cin_blocks * segs[s].kt * segs[s].kh * segs[s].kw;
+  }
+  p.sgn = sgn;
+  p.b_mn_major = b_mn_major;
+  p.bw_log2 = ilog2(bw);
+  p.bh_log2 = ilog2(bh);
+  p.bt_log2 = ilog2(bt);
+  p.tiles_w = W / bw;
+  p.tiles_h = H / bh;
+  p.tiles_t = T / bt;
+  p.T = T;
+  p.H = H;
+  p.W = W;
+  p.num_m_tiles = N * p.tiles_w * p.tiles_h * p.tiles_t;
+  p.block_n = pick_block_n(n_out, p.num_m_tiles, b_mn_major != 0);
+  p.num_n_tiles = (n_out + p.block_n - 1) / p.block_n;
+  p.n_out = n_out;
+  p.ldo = n_out;
+  p.out = out;
+  p.out_f32 = out_f32;
+  p.vec_ok = out_f32 ? (n_out % 4 == 0) : (n_out % 8 == 0);
+  p.bias0 = bias0;
+  p.bias1 = bias1;
+  const int stage_bytes = kABytes + p.block_n * kBlockK * 2;
+  int stages = (220 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.num_stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+  CUtensorMap mapA0, mapA1, mapB;
+  {
+    uint64_t dims[5] = {(uint64_t)c0, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)c0 * 2, (uint64_t)W * c0 * 2, (uint64_t)H * W * c0 * 2, (uint64_t)T * H * W * c0 * 2};
+    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    int r = make_tmap_bf16(&mapA0, a0, 5, dims, str, box);
+    if (r != OG_OK) return r;
+  }
+  if (nseg > 1) {
+    uint64_t dims[5] = {(uint64_t)c1, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)c1 * 2, (uint64_t)W * c1 * 2, (uint64_t)H * W * c1 * 2, (uint64_t)T * H * W * c1 * 2};
+    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    int r = make_tmap_bf16(&mapA1, a1, 5, dims, str, box);
+    if (r != OG_OK) return r;
+  } else {
+    mapA1 = mapA0;
+  }
+  const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(w) + k_off;
+  if (!b_mn_major) {
+    // rows = output channels, contiguous k
+    uint64_t ktot = (uint64_t)p.num_kb * kBlockK;
+    uint64_t dims[2] = {ktot, (uint64_t)n_out};
+    uint64_t str[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {kBlockK, (uint32_t)p.block_n};
+    int r = make_tmap_bf16(&mapB, wb, 2, dims, str, box);
+    if (r != OG_OK) return r;
+  } else {
+    // w[co][tap][ci] viewed as (ci, tap, co): a (64,1,64) box lands as one [64 co rows][64 ci] panel
+    uint64_t dims[3] = {(uint64_t)n_out, (uint64_t)b_ntaps, (uint64_t)b_rows};
+    uint64_t str[2] = {(uint64_t)n_out * 2, (uint64_t)ldw * 2};
+    uint32_t box[3] = {64, 1, 64};
+    int r = make_tmap_bf16(&mapB, wb, 3, dims, str, box);
+    if (r != OG_OK) return r;
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  og_conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapB, p);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+}  // namespace og
+
+extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1,
+                             int c1, const void* w, int ldw, const float* bias0, const float* bias1, void* out,
+                             int out_f32, int N, int T, int H, int W, int cout, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(x0 && w && out, "conv3d_fwd: null pointer");
+  OG_REQUIRE(c0 > 0 && c0 % 64 == 0, "conv3d_fwd: c0=%d must be a positive multiple of 64 (use the im2col path)", c0);
+  OG_REQUIRE(!x1 || (c1 > 0 && c1 % 64 == 0), "conv3d_fwd: c1=%d must be a multiple of 64", c1);
+  OG_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && pt >= 0 && ph >= 0 && pw >= 0 && pt < kt && ph < kh && pw < kw,
+             "conv3d_fwd: bad kernel/padding (%d,%d,%d)/(%d,%d,%d)", kt, kh, kw, pt, ph, pw);
+  const int ktot = kt * kh * kw * c0 + (x1 ? c1 : 0);
+  OG_REQUIRE(ldw >= ktot && ldw % 8 == 0, "conv3d_fwd: ldw=%d must be >= %d and a multiple of 8", ldw, ktot);
+  IgemmSeg segs[2];
+  segs[0] = IgemmSeg{c0 / 64, kt, kh, kw, pt, ph, pw};
+  segs[1] = IgemmSeg{c1 / 64, 1, 1, 1, 0, 0, 0};
+  return launch_igemm(x0, c0, x1, c1, segs, x1 ? 2 : 1, +1, w, ldw, 0, 0, 0, 0, bias0, bias1, out, out_f32, N, T, H, W,
+                      cout, (cudaStream_t)stream);
+}
+
+extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int k_off, int kt, int kh,
+                               int kw, int pt, int ph, int pw, void* dx, int dx_f32, int N, int T, int H, int W,
+                               int cin, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(dy && w && dx, "conv3d_dgrad: null pointer");
+  OG_REQUIRE(cout > 0 && cout % 64 == 0, "conv3d_dgrad: cout=%d must be a multiple of 64", cout);
+  OG_REQUIRE(cin > 0 && cin % 64 == 0, "conv3d_dgrad: cin=%d must be a multiple of 64", cin);
+  OG_REQUIRE(k_off % 8 == 0 && ldw % 8 == 0, "conv3d_dgrad: k_off/ldw must be multiples of 8");
+  OG_REQUIRE(w_rows > 0 && w_rows <= cout, "conv3d_dgrad: w_rows=%d must be in (0, cout]", w_rows);
+  IgemmSeg segs[1];
+  segs[0] = IgemmSeg{cout / 64, kt, kh, kw, pt, ph, pw};
+  return launch_igemm(dy, cout, nullptr, 0, segs, 1, -1, w, ldw, k_off, 1, w_rows, kt * kh * kw, nullptr, nullptr, dx,
+                      dx_f32, N, T, H, W, cin, (cudaStream_t)stream);
+}

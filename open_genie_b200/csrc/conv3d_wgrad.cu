@@ -1,0 +1,266 @@
+// conv3d_wgrad.cu — weight gradient of the stride-1 3-D convolution on tcgen05 tensor cores.
+//
+//   dW[co][tap][ci] += sum_v dY[v][co] * X[v + tap - pad][ci]          (v = voxel (n,t,h,w))
+//
+// As a GEMM the reduction dimension is the voxel index, and both operands are stored with the
+// NON-reduced dimension contiguous (channels-last), i.e. both are "MN-major" UMMA operands:
+//   A tile = dY box  : [co/64 panel][64 voxel rows][64 co]   (TMA 5-D box, 128-byte swizzle)
+//   B tile = X  box  : [ci/64 panel][64 voxel rows][64 ci]   (same box shifted by the tap; OOB -> 0)
+// so no transposed copy of activations or gradients is ever made. Each filter tap owns its own fp32
+// accumulator block in TMEM (up to 4 taps x 128 columns = all 512 columns); the dY tile of a k-step is
+// loaded once and reused by every tap of the group. The voxel range is split across CTAs (split-K) and
+// partial sums are combined with fp32 red.global.add into dW, which the caller zeroes.
+//
+// Replaces autograd's conv3d weight-gradient reached from genie/module/video.py:192,609-629,599-603 and
+// genie/module/attention.py:429-438 during loss.backward().
+#include "og_host.cuh"
+#include "og_ptx.cuh"
+
+namespace og {
+extern std::atomic<uint64_t> g_launches;
+
+struct WgradParams {
+  int kt, kh, kw, pt, ph, pw;
+  int ntaps, taps_per_group, num_groups, splitk;
+  int block_n;  // ci tile (64 or 128)
+  int bw_log2, bh_log2, bt_log2;
+  int tiles_w, tiles_h, tiles_t;
+  int num_ksteps;  // 64-voxel boxes in the whole tensor
+  int cin, cout;
+  float* dw;
+  long long ld_dw;
+  int a_stages, b_stages;
+};
+
+static constexpr int kWThreads = 192;
+static constexpr int kVox = 64;                 // voxels (K rows) per k-step
+static constexpr int kPanelBytes = kVox * 128;  // one 64-channel panel of a box: 8 KiB
+static constexpr int kWABytes = 2 * kPanelBytes;  // 128 output channels
+static constexpr int kWMaxStages = 12;
+
+__global__ void __launch_bounds__(kWThreads, 1)
+    og_conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX,
+                         const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = (p.block_n / 64) * kPanelBytes;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.a_stages * kWABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.b_stages * b_bytes);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = bars + kWMaxStages;
+  uint64_t* full_b = bars + 2 * kWMaxStages;
+  uint64_t* empty_b = bars + 3 * kWMaxStages;
+  uint64_t* tmem_full = bars + 4 * kWMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kWMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 128;
+  const int ci0 = blockIdx.y * p.block_n;
+  const int group = blockIdx.z / p.splitk;
+  const int split = blockIdx.z - group * p.splitk;
+  const int tap0 = group * p.taps_per_group;
+  const int ntap = min(p.taps_per_group, p.ntaps - tap0);
+  // contiguous k-step range of this split
+  const int ks_begin = (int)(((long long)p.num_ksteps * split) / p.splitk);
+  const int ks_end = (int)(((long long)p.num_ksteps * (split + 1)) / p.splitk);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapDY);
+    tma_prefetch_desc(&mapX);
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      const int per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
+        const int n = ks / per_sample;
+        int r = ks - n * per_sample;
+        const int w0 = (r % p.tiles_w) << p.bw_log2;
+        r /= p.tiles_w;
+        const int h0 = (r % p.tiles_h) << p.bh_log2;
+        const int t0 = (r / p.tiles_h) << p.bt_log2;
+        mbar_wait(&empty_a[sa], pha ^ 1);
+        mbar_expect_tx(&full_a[sa], kWABytes);
+        tma_load_5d(smem_a + sa * kWABytes, &mapDY, &full_a[sa], co0, w0, h0, t0, n);
+        tma_load_5d(smem_a + sa * kWABytes + kPanelBytes, &mapDY, &full_a[sa], co0 + 64, w0, h0, t0, n);
+        if (++sa == p.a_stages) {
+          sa = 0;
+          pha ^= 1;
+        }
+        for (int j = 0; j < ntap; ++j) {
+          const int tap = tap0 + j;
+          const int it = tap / (p.kh * p.kw);
+          const int ih = (tap / p.kw) % p.kh;
+          const int iw = tap % p.kw;
+          mbar_wait(&empty_b[sb], phb ^ 1);
+          mbar_expect_tx(&full_b[sb], (uint32_t)b_bytes);
+          for (int pp = 0; pp < p.block_n / 64; ++pp)
+            tma_load_5d(smem_b + sb * b_bytes + pp * kPanelBytes, &mapX, &full_b[sb], ci0 + pp * 64, w0 + iw - p.pw,
+                        h0 + ih - p.ph, t0 + it - p.pt, n);
+          if (++sb == p.b_stages) {
+            sb = 0;
+            phb ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.block_n, 1u, 1u);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int ks = ks_begin; ks < ks_end; ++ks) {
+        mbar_wait(&full_a[sa], pha);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + sa * kWABytes);
+        for (int j = 0; j < ntap; ++j) {
+          mbar_wait(&full_b[sb], phb);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(smem_b + sb * b_bytes);
+          const uint32_t d_tmem = tmem_base + j * p.block_n;
+#pragma unroll
+          for (int k = 0; k < kVox / 16; ++k) {
+            // MN-major panels [panel][64 k-rows][128 B]: 16 k-rows = 2048 B, panel stride = 8192 B
+            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, kPanelBytes, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, kPanelBytes, 1024);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (ks > ks_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_b[sb]);
+          if (++sb == p.b_stages) {
+            sb = 0;
+            phb ^= 1;
+          }
+        }
+        umma_commit(&empty_a[sa]);
+        if (++sa == p.a_stages) {
+          sa = 0;
+          pha ^= 1;
+        }
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int j = 0; j < ntap; ++j) {
+      const int tap = tap0 + j;
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + j * p.block_n + c + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+        if (co < p.cout) {
+          float* dst = p.dw + (long long)co * p.ld_dw + (long long)tap * p.cin + ci0 + c;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj)
+            if (ci0 + c + jj < p.cin) atomicAdd(dst + jj, __uint_as_float(v[jj]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace og
+
+extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt,
+                               int kh, int kw, int pt, int ph, int pw, int N, int T, int H, int W,
+                               og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(dy && x && dw, "conv3d_wgrad: null pointer");
+  OG_REQUIRE(cin > 0 && cin % 64 == 0, "conv3d_wgrad: cin=%d must be a multiple of 64", cin);
+  OG_REQUIRE(cout > 0 && cout % 8 == 0, "conv3d_wgrad: cout=%d must be a multiple of 8 (TMA row stride)", cout);
+  OG_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && pt >= 0 && ph >= 0 && pw >= 0 && pt < kt && ph < kh && pw < kw,
+             "conv3d_wgrad: bad kernel/padding");
+  int bw, bh, bt;
+  if (!choose_voxel_box(kVox, T, H, W, &bw, &bh, &bt)) {
+    set_error("conv3d_wgrad: cannot tile T=%d H=%d W=%d into 64-voxel boxes", T, H, W);
+    return OG_ERR_UNSUPPORTED_SHAPE;
+  }
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.kt = kt; p.kh = kh; p.kw = kw; p.pt = pt; p.ph = ph; p.pw = pw;
+  p.ntaps = kt * kh * kw;
+  p.block_n = (cin % 128 == 0) ? 128 : 64;
+  p.taps_per_group = 512 / p.block_n;
+  if (p.taps_per_group > 4) p.taps_per_group = 4;  // smem budget of the B ring
+  if (p.taps_per_group > p.ntaps) p.taps_per_group = p.ntaps;
+  p.num_groups = (p.ntaps + p.taps_per_group - 1) / p.taps_per_group;
+  p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh); p.bt_log2 = ilog2(bt);
+  p.tiles_w = W / bw; p.tiles_h = H / bh; p.tiles_t = T / bt;
+  p.num_ksteps = N * p.tiles_w * p.tiles_h * p.tiles_t;
+  p.cin = cin; p.cout = cout; p.dw = dw; p.ld_dw = ld_dw;
+  const int co_tiles = (cout + 127) / 128;
+  const int ci_tiles = cin / p.block_n;
+  const int base_ctas = co_tiles * ci_tiles * p.num_groups;
+  int splitk = (2 * num_sms() + base_ctas - 1) / base_ctas;  // ~2 CTAs' worth of work items per SM
+  if (splitk < 1) splitk = 1;
+  // keep at least 8 k-steps per CTA so the pipeline fill / epilogue atomics are amortised
+  int max_split = p.num_ksteps / 8;
+  if (max_split < 1) max_split = 1;
+  if (splitk > max_split) splitk = max_split;
+  if (splitk > p.num_ksteps) splitk = p.num_ksteps;
+  p.splitk = splitk;
+  const int b_bytes = (p.block_n / 64) * kPanelBytes;
+  p.a_stages = 3;
+  p.b_stages = (int)((216 * 1024 - p.a_stages * kWABytes) / b_bytes);
+  if (p.b_stages > kWMaxStages) p.b_stages = kWMaxStages;
+  const size_t smem_bytes = (size_t)p.a_stages * kWABytes + (size_t)p.b_stages * b_bytes + 1024 + 512;
+
+  CUtensorMap mapDY, mapX;
+  {
+    uint64_t dims[5] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2,
+                       (uint64_t)T * H * W * cout * 2};
+    uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    int r = make_tmap_bf16(&mapDY, dy, 5, dims, str, box);
+    if (r != OG_OK) return r;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2,
+                       (uint64_t)T * H * W * cin * 2};
+    uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    int r = make_tmap_bf16(&mapX, x, 5, dims, str, box);
+    if (r != OG_OK) return r;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(co_tiles, ci_tiles, p.num_groups * p.splitk);
+  og_conv_wgrad_kernel<<<grid, kWThreads, smem_bytes, (cudaStream_t)stream>>>(mapDY, mapX, p);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}

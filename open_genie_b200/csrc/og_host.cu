@@ -1,0 +1,102 @@
+// og_host.cu — error reporting, TMA descriptor encoding, device queries, ABI housekeeping.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "og_host.cuh"
+
+namespace og {
+
+static thread_local char g_err[512] = {0};
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver / GPU?)");
+    return OG_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+              rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+    return OG_ERR_CUDA;
+  }
+  return OG_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+bool choose_voxel_box(int vox, int T, int H, int W, int* bw, int* bh, int* bt) {
+  // widest-first: fill W, then H, then T with power-of-two factors of `vox`
+  int rem = vox;
+  int w = 1;
+  while (w * 2 <= rem && W % (w * 2) == 0) w *= 2;
+  rem /= w;
+  int h = 1;
+  while (h * 2 <= rem && H % (h * 2) == 0) h *= 2;
+  rem /= h;
+  int t = 1;
+  while (t * 2 <= rem && T % (t * 2) == 0) t *= 2;
+  rem /= t;
+  if (rem != 1) return false;
+  // a box that is narrower than W must still tile H/T exactly (guaranteed by the divisibility loop)
+  if (w > 256 || h > 256 || t > 256) return false;
+  *bw = w;
+  *bh = h;
+  *bt = t;
+  return true;
+}
+
+}  // namespace og
+
+extern "C" {
+const char* og_last_error(void) { return og::g_err; }
+int og_abi_version(void) { return 1; }
+int og_compiled_sm(void) { return 100; }
+uint64_t og_launch_count(void) { return og::g_launches.load(); }
+}
