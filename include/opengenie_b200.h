@@ -81,6 +81,130 @@ int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw
 int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt, int kh,
                     int kw, int pt, int ph, int pw, int N, int T, int H, int W, og_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm / AdaptiveGroupNorm (+SiLU), NDHWC bf16, HBM-bound passes
+ * Replaces F.group_norm / nn.GroupNorm + nn.SiLU (genie/module/video.py:607-608,622-623;
+ * tokenizer.py:75-79,163-167; genie/module/misc.py:93) and AdaptiveGroupNorm.forward
+ * (genie/module/norm.py:55-69), forward and backward.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* sums[n][g] = (sum x, sum x^2) over the group, accumulated in fp64 (caller zeroes sums: N*G*2 doubles).
+ * x: bf16 [N,V,C]; C % 8 == 0, (C/G) % 8 == 0, G <= 64. */
+int og_gn_stats(const void* x, int N, int64_t V, int C, int G, double* sums, og_stream_t stream);
+
+/* Folds statistics, affine (gamma, beta: fp32 [C] or NULL) and the optional AdaGN modulation
+ * (cond_scale, cond_shift: fp32 [N,C] or NULL) into y = x*A[n][c] + B[n][c]; also writes
+ * mean_rstd[n][g] = (mean, rstd) for the backward pass. */
+int og_gn_finalize(const double* sums, int N, int C, int G, int64_t V, float eps, const float* gamma,
+                   const float* beta, const float* cond_scale, const float* cond_shift, float* A, float* B,
+                   float* mean_rstd, og_stream_t stream);
+
+/* y = act(x*A + B); act: 0 = identity, 1 = SiLU. x,y: bf16 [N,V,C]. */
+int og_affine_act_fwd(const void* x, const float* A, const float* B, void* y, int N, int64_t V, int C, int act,
+                      og_stream_t stream);
+
+/* S[n][c] = (sum_v dpre, sum_v dpre*x), dpre = dy * act'(x*A+B). Caller zeroes S (N*C*2 floats). */
+int og_affine_act_bwd_reduce(const void* dy, const void* x, const float* A, const float* B, int act, float* S,
+                             int N, int64_t V, int C, og_stream_t stream);
+
+/* Turns S into the per-(n,c) coefficients of dx = A*dpre + Q*x + R and the parameter gradients:
+ * dgamma/dbeta [C] are ACCUMULATED (+=); dcond_scale/dcond_shift [N,C] are written. Any of the four may
+ * be NULL. */
+int og_gn_bwd_finalize(const float* S, const float* mean_rstd, const float* gamma, const float* beta,
+                       const float* cond_scale, int N, int C, int G, int64_t V, float* Q, float* R, float* dgamma,
+                       float* dbeta, float* dcond_scale, float* dcond_shift, og_stream_t stream);
+
+/* dx = A*dpre + Q*x + R (+ add). Q,R NULL => pure activation backward. add: optional bf16 [N,V,C]. */
+int og_affine_act_bwd_apply(const void* dy, const void* x, const float* A, const float* B, const float* Q,
+                            const float* R, const void* add, void* dx, int act, int N, int64_t V, int C,
+                            og_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * layout / data movement
+ * ---------------------------------------------------------------------------------------------- */
+
+/* NCDHW fp32 (the reference's tensor format at every public method, e.g. tokenizer.py:307-330) to the
+ * internal NDHWC format (bf16, or fp32 when y_f32) and back. V = T*H*W. */
+int og_ncdhw_f32_to_ndhwc(const float* x, void* y, int y_f32, int N, int C, int64_t V, og_stream_t stream);
+int og_ndhwc_to_ncdhw_f32(const void* x, int x_f32, float* y, int N, int C, int64_t V, og_stream_t stream);
+
+/* Depth-to-space-time: Rearrange('b (c p q r) t h w -> b c (t p) (h q) (w r)') of
+ * DepthToSpaceTimeUpsample (genie/module/video.py:403-408). x: bf16 [N,T,H,W,c*p*q*r] un-shuffled,
+ * y: bf16 [N,T*p,H*q,W*r,c] shuffled. inverse=0 reads x writes y; inverse=1 reads y writes x (backward). */
+int og_pixel_shuffle3d(const void* x, void* y, int inverse, int N, int T, int H, int W, int c, int p, int q, int r,
+                       og_stream_t stream);
+
+/* Explicit im2col for the layers the implicit-GEMM kernel does not take directly: strided
+ * CausalConv3d (SpaceTimeDownsample, video.py:477-483) and Cin not a multiple of 64.
+ * Causal geometry (video.py:154-164): pt is the FRONT time pad only; ph/pw are symmetric.
+ * col: bf16 [N*To*Ho*Wo][kpad], k = tap*C + ci, zero beyond kt*kh*kw*C. col2im is its adjoint. */
+int og_im2col3d(const void* x, void* col, int N, int T, int H, int W, int C, int kt, int kh, int kw, int st, int sh,
+                int sw, int pt, int ph, int pw, int kpad, og_stream_t stream);
+int og_col2im3d(const void* dcol, void* dx, int dx_f32, int N, int T, int H, int W, int C, int kt, int kh, int kw,
+                int st, int sh, int sw, int pt, int ph, int pw, int kpad, og_stream_t stream);
+
+/* mse_loss (tokenizer.py:364, action.py:166): loss_sum += sum (rec - tgt)^2 ; rec NDHWC fp32, tgt NCDHW fp32.
+ * Backward writes gscale * 2 (rec - tgt) / numel as bf16 NDHWC with cpad >= C channels (zero padded) so it
+ * can feed og_conv3d_dgrad / og_conv3d_wgrad directly. gscale: device scalar or NULL (= 1). */
+int og_mse_fwd(const float* rec_ndhwc, const float* tgt_ncdhw, int N, int C, int64_t V, float* loss_sum,
+               og_stream_t stream);
+int og_mse_bwd(const float* rec_ndhwc, const float* tgt_ncdhw, const float* gscale, int N, int C, int cpad,
+               int64_t V, void* drec, og_stream_t stream);
+
+/* out[c] += sum_rows x[row][c] (conv bias gradient). x: bf16 [rows][ld]. */
+int og_colsum(const void* x, int64_t rows, int C, int ld, float* out, og_stream_t stream);
+/* y[row][0:cd] = x[row][0:cs] zero-padded / truncated; x fp32 or bf16, y bf16. */
+int og_pad_channels(const void* x, int x_f32, void* y, int64_t rows, int cs, int cd, og_stream_t stream);
+
+/* dst[row*dst_ld + c] = bf16(src[row*src_ld + c]) for c < cols: refreshes the bf16 operand copy of a
+ * conv weight (the cast torch.autocast performs on every conv call, config/tokenize.yaml:78) into one
+ * segment of a packed [cout][ldw] weight matrix. src: fp32 or bf16. */
+int og_copy_rows_to_bf16(const void* src, int src_f32, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                         int cols, og_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Lookup-Free Quantization (genie/module/quantization.py:77-133)
+ * ---------------------------------------------------------------------------------------------- */
+size_t og_lfq_workspace_bytes(int64_t ntok, int D);
+
+/* x: fp32 [ntok][ldx] (first D columns), the tensor AFTER proj_inp / 'b d ... -> b ... d'.
+ * out_f32 [ntok][D] and/or out_bf16 [ntok][ld_bf16] (zero padded): sign(x) in eval mode, the straight-
+ * through value x + (sign(x) - x) in training mode (line 101). idx: int64 [ntok], MSB-first bit pack (98).
+ * training != 0 additionally writes loss[0] =
+ *   w_entropy * (mean_n H(p_n) + w_div * H(mean_n p_n)) + w_commit * mse(x, sign x)      (lines 116-131)
+ * and fills the workspace (og_lfq_workspace_bytes) that og_lfq_bwd consumes. */
+int og_lfq_fwd(const float* x, int ldx, int64_t ntok, int D, float beta, int training, float w_commit,
+               float w_entropy, float w_div, float* out_f32, void* out_bf16, int ld_bf16, int64_t* idx, float* loss,
+               void* workspace, og_stream_t stream);
+
+/* dx = gloss * dloss/dx + dout (straight-through). gloss: device scalar (NULL = 1); dout: fp32
+ * [ntok][ld_dout] or NULL. Writes dx_f32 and/or dx_bf16, both [ntok][ld_dx] with columns >= D zeroed. */
+int og_lfq_bwd(const float* x, int ldx, int64_t ntok, int D, float beta, float w_commit, float w_entropy,
+               const float* gloss, const float* dout, int ld_dout, float* dx_f32, void* dx_bf16, int ld_dx,
+               void* workspace, og_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fused multi-tensor AdamW (genie/tokenizer.py:437-442) + bf16 operand refresh
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct og_adamw_tensor {
+  float* p;        /* fp32 master weights, n elements */
+  const float* g;  /* fp32 gradient or NULL (then only the bf16 copy is refreshed) */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  void* p_bf16;    /* optional bf16 destination: element i -> [(i / row_len) * dst_ld + i % row_len] */
+  int64_t n;
+  int64_t row_len;
+  int64_t dst_ld;
+} og_adamw_tensor;
+
+int og_adamw_chunk_elems(void);
+/* table_dev: device array of tensors; chunk_tensor_dev / chunk_index_dev: for every chunk of
+ * og_adamw_chunk_elems() elements, which tensor and which chunk inside it. step >= 1.
+ * grad_scale_dev: optional device scalar multiplied into every gradient (e.g. 1/world_size). */
+int og_adamw_step(const og_adamw_tensor* table_dev, const int* chunk_tensor_dev, const int* chunk_index_dev,
+                  int num_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  const float* grad_scale_dev, og_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

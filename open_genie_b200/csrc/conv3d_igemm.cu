@@ -38,9 +38,9 @@ struct IgemmParams {
   int b_mn_major;  // 0: B tile is [n rows][64 k] (K-major); 1: B tile is [k rows][n] in 64-wide panels (MN-major)
   int block_n;     // UMMA N (16..256)
   int num_n_tiles, num_m_tiles;
-  int bw_log2, bh_log2, bt_log2;  // M tile = 2^bw x 2^bh x 2^bt voxels (product 128)
-  int tiles_w, tiles_h, tiles_t;  // M tiles per sample along each axis
-  int T, H, W;
+  int bw_log2, bh_log2, bt_log2, bn_log2;  // M tile = 2^bw x 2^bh x 2^bt x 2^bn voxels (product 128)
+  int tiles_w, tiles_h, tiles_t;           // M tiles along each axis (ceil)
+  int N, T, H, W;
   int n_out;      // valid output channels
   long long ldo;  // output row stride in elements
   void* out;
@@ -61,14 +61,15 @@ static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 192;
 
 struct TileCoord {
-  int n, t0, h0, w0;
+  int n0, t0, h0, w0;
 };
 
 __device__ __forceinline__ TileCoord decode_m_tile(const IgemmParams& p, int m_tile) {
   TileCoord c;
   int per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
-  c.n = m_tile / per_sample;
-  int r = m_tile - c.n * per_sample;
+  const int tn = m_tile / per_sample;
+  c.n0 = tn << p.bn_log2;
+  int r = m_tile - tn * per_sample;
   int tw = r % p.tiles_w;
   r /= p.tiles_w;
   int th = r % p.tiles_h;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                   uint8_t* sa = smem + stage * stage_bytes;
                   uint8_t* sb = sa + kABytes;
                   mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                  tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, cw, ch, ct, tc.n);
+                  tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, cw, ch, ct, tc.n0);
                   if (!p.b_mn_major) {
                     tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
                   } else {
@@ -216,8 +217,11 @@ __global__ void __launch_bounds__(kThreads, 1)
       const TileCoord tc = decode_m_tile(p, m_tile);
       const int dw = row & ((1 << p.bw_log2) - 1);
       const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
-      const int dt = row >> (p.bw_log2 + p.bh_log2);
-      const long long vox = (((long long)tc.n * p.T + (tc.t0 + dt)) * p.H + (tc.h0 + dh)) * p.W + (tc.w0 + dw);
+      const int dt = (row >> (p.bw_log2 + p.bh_log2)) & ((1 << p.bt_log2) - 1);
+      const int dn = row >> (p.bw_log2 + p.bh_log2 + p.bt_log2);
+      const int vn = tc.n0 + dn, vt = tc.t0 + dt, vh = tc.h0 + dh, vw = tc.w0 + dw;
+      const bool row_ok = vn < p.N && vt < p.T && vh < p.H && vw < p.W;  // partial boxes: masked store
+      const long long vox = (((long long)vn * p.T + vt) * p.H + vh) * p.W + vw;
       const int col0 = n_tile * p.block_n;
 
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         tmem_ld_wait();
         const int cbase = col0 + c;
-        if (cbase >= p.n_out) continue;
+        if (cbase >= p.n_out || !row_ok) continue;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -318,11 +322,8 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
                         int b_ntaps, const float* bias0, const float* bias1, void* out, int out_f32, int N, int T,
                         int H, int W, int n_out, cudaStream_t stream) {
   OG_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0 && n_out > 0, "conv3d: empty problem");
-  int bw, bh, bt;
-  if (!choose_voxel_box(kBlockM, T, H, W, &bw, &bh, &bt)) {
-    set_error("conv3d: cannot tile T=%d H=%d W=%d into 128-voxel boxes (need power-of-two factors)", T, H, W);
-    return OG_ERR_UNSUPPORTED_SHAPE;
-  }
+  int bw, bh, bt, bn;
+  choose_voxel_box(kBlockM, N, T, H, W, &bw, &bh, &bt, &bn);
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   p.nseg = nseg;
@@ -336,13 +337,15 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   p.bw_log2 = ilog2(bw);
   p.bh_log2 = ilog2(bh);
   p.bt_log2 = ilog2(bt);
-  p.tiles_w = W / bw;
-  p.tiles_h = H / bh;
-  p.tiles_t = T / bt;
+  p.bn_log2 = ilog2(bn);
+  p.tiles_w = (W + bw - 1) / bw;
+  p.tiles_h = (H + bh - 1) / bh;
+  p.tiles_t = (T + bt - 1) / bt;
+  p.N = N;
   p.T = T;
   p.H = H;
   p.W = W;
-  p.num_m_tiles = N * p.tiles_w * p.tiles_h * p.tiles_t;
+  p.num_m_tiles = ((N + bn - 1) / bn) * p.tiles_w * p.tiles_h * p.tiles_t;
   p.block_n = pick_block_n(n_out, p.num_m_tiles, b_mn_major != 0);
   p.num_n_tiles = (n_out + p.block_n - 1) / p.block_n;
   p.n_out = n_out;
@@ -362,14 +365,14 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   {
     uint64_t dims[5] = {(uint64_t)c0, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)c0 * 2, (uint64_t)W * c0 * 2, (uint64_t)H * W * c0 * 2, (uint64_t)T * H * W * c0 * 2};
-    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, (uint32_t)bn};
     int r = make_tmap_bf16(&mapA0, a0, 5, dims, str, box);
     if (r != OG_OK) return r;
   }
   if (nseg > 1) {
     uint64_t dims[5] = {(uint64_t)c1, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)c1 * 2, (uint64_t)W * c1 * 2, (uint64_t)H * W * c1 * 2, (uint64_t)T * H * W * c1 * 2};
-    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, (uint32_t)bn};
     int r = make_tmap_bf16(&mapA1, a1, 5, dims, str, box);
     if (r != OG_OK) return r;
   } else {

@@ -23,7 +23,7 @@ struct WgradParams {
   int kt, kh, kw, pt, ph, pw;
   int ntaps, taps_per_group, num_groups, splitk;
   int block_n;  // ci tile (64 or 128)
-  int bw_log2, bh_log2, bt_log2;
+  int bw_log2, bh_log2, bt_log2, bn_log2;
   int tiles_w, tiles_h, tiles_t;
   int num_ksteps;  // 64-voxel boxes in the whole tensor
   int cin, cout;
@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(kWThreads, 1)
       uint32_t pha = 0, phb = 0;
       const int per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
       for (int ks = ks_begin; ks < ks_end; ++ks) {
-        const int n = ks / per_sample;
-        int r = ks - n * per_sample;
+        const int n = (ks / per_sample) << p.bn_log2;
+        int r = ks % per_sample;
         const int w0 = (r % p.tiles_w) << p.bw_log2;
         r /= p.tiles_w;
         const int h0 = (r % p.tiles_h) << p.bh_log2;
@@ -201,11 +201,8 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
   OG_REQUIRE(cout > 0 && cout % 8 == 0, "conv3d_wgrad: cout=%d must be a multiple of 8 (TMA row stride)", cout);
   OG_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && pt >= 0 && ph >= 0 && pw >= 0 && pt < kt && ph < kh && pw < kw,
              "conv3d_wgrad: bad kernel/padding");
-  int bw, bh, bt;
-  if (!choose_voxel_box(kVox, T, H, W, &bw, &bh, &bt)) {
-    set_error("conv3d_wgrad: cannot tile T=%d H=%d W=%d into 64-voxel boxes", T, H, W);
-    return OG_ERR_UNSUPPORTED_SHAPE;
-  }
+  int bw, bh, bt, bn;
+  choose_voxel_box(kVox, N, T, H, W, &bw, &bh, &bt, &bn);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.kt = kt; p.kh = kh; p.kw = kw; p.pt = pt; p.ph = ph; p.pw = pw;
@@ -215,9 +212,9 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
   if (p.taps_per_group > 4) p.taps_per_group = 4;  // smem budget of the B ring
   if (p.taps_per_group > p.ntaps) p.taps_per_group = p.ntaps;
   p.num_groups = (p.ntaps + p.taps_per_group - 1) / p.taps_per_group;
-  p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh); p.bt_log2 = ilog2(bt);
-  p.tiles_w = W / bw; p.tiles_h = H / bh; p.tiles_t = T / bt;
-  p.num_ksteps = N * p.tiles_w * p.tiles_h * p.tiles_t;
+  p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh); p.bt_log2 = ilog2(bt); p.bn_log2 = ilog2(bn);
+  p.tiles_w = (W + bw - 1) / bw; p.tiles_h = (H + bh - 1) / bh; p.tiles_t = (T + bt - 1) / bt;
+  p.num_ksteps = ((N + bn - 1) / bn) * p.tiles_w * p.tiles_h * p.tiles_t;
   p.cin = cin; p.cout = cout; p.dw = dw; p.ld_dw = ld_dw;
   const int co_tiles = (cout + 127) / 128;
   const int ci_tiles = cin / p.block_n;
@@ -241,7 +238,7 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
     uint64_t dims[5] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2,
                        (uint64_t)T * H * W * cout * 2};
-    uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, (uint32_t)bn};
     int r = make_tmap_bf16(&mapDY, dy, 5, dims, str, box);
     if (r != OG_OK) return r;
   }
@@ -249,7 +246,7 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
     uint64_t dims[5] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2,
                        (uint64_t)T * H * W * cin * 2};
-    uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, 1};
+    uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, (uint32_t)bn};
     int r = make_tmap_bf16(&mapX, x, 5, dims, str, box);
     if (r != OG_OK) return r;
   }

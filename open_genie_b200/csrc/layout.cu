@@ -1,0 +1,417 @@
+// layout.cu — data-movement kernels around the conv stack (all HBM-bound, coalesced on the
+// channel-contiguous side, 16-byte vectors where the channel count allows):
+//   * NCDHW fp32 <-> NDHWC bf16/fp32 casts at the Python boundary (the reference keeps NCDHW fp32
+//     everywhere; the product keeps NDHWC bf16 between kernels)
+//   * depth-to-space-time pixel shuffle 'b (c p q r) t h w -> b c (t p) (h q) (w r)' and its inverse
+//     (genie/module/video.py:403-408)
+//   * explicit im2col / col2im for the few layers the implicit-GEMM kernel does not take directly:
+//     strided CausalConv3d (SpaceTimeDownsample, video.py:477-483) and convs whose Cin is not a
+//     multiple of 64 (3 -> C input projections, 18 -> 512 decoder stem)
+//   * mse_loss forward / backward (tokenizer.py:364, action.py:166), bias gradient (column sums)
+#include "og_host.cuh"
+#include "og_ptx.cuh"
+
+namespace og {
+extern std::atomic<uint64_t> g_launches;
+
+static int ew_blocks(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = (long long)num_sms() * 32;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// NCDHW f32 -> NDHWC (bf16 or f32), via a 32x32 smem transpose over (channel, voxel)
+template <typename OutT>
+__global__ void og_ncdhw_to_ndhwc_kernel(const float* __restrict__ x, OutT* __restrict__ y, int C, long long V) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long v = v0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && v < V) ? x[((long long)n * C + c) * V + v] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long v = v0 + i;
+    const int c = c0 + threadIdx.x;
+    if (c < C && v < V) {
+      const float val = tile[threadIdx.x][i];
+      if constexpr (sizeof(OutT) == 2)
+        y[((long long)n * V + v) * C + c] = __float2bfloat16_rn(val);
+      else
+        y[((long long)n * V + v) * C + c] = val;
+    }
+  }
+}
+
+template <typename InT>
+__global__ void og_ndhwc_to_ncdhw_kernel(const InT* __restrict__ x, float* __restrict__ y, int C, long long V) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long v = v0 + i;
+    const int c = c0 + threadIdx.x;
+    float val = 0.f;
+    if (c < C && v < V) {
+      if constexpr (sizeof(InT) == 2)
+        val = __bfloat162float(x[((long long)n * V + v) * C + c]);
+      else
+        val = x[((long long)n * V + v) * C + c];
+    }
+    tile[i][threadIdx.x] = val;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long v = v0 + threadIdx.x;
+    if (c < C && v < V) y[((long long)n * C + c) * V + v] = tile[threadIdx.x][i];
+  }
+}
+
+// pixel shuffle. forward: x [N,T,H,W,c*p*q*r] -> y [N,T*p,H*q,W*r,c]; channel index of x = ((cc*p+pp)*q+qq)*r+rr
+// One thread per (output voxel, 8-channel... ) the gather side is strided by p*q*r, so go scalar on x and
+// vector on y: thread handles 8 consecutive output channels.
+__global__ void og_pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int T,
+                                        int H, int W, int c, int p, int q, int r, long long total_vec, int inverse) {
+  const int cv = c >> 3;
+  const int pqr = p * q * r;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v8 = (int)(i % cv);
+    long long o = i / cv;  // output voxel index over [N, T*p, H*q, W*r]
+    const int wo = (int)(o % (W * r));
+    o /= (W * r);
+    const int ho = (int)(o % (H * q));
+    o /= (H * q);
+    const int to = (int)(o % (T * p));
+    const int n = (int)(o / (T * p));
+    const int t = to / p, pp = to % p, h = ho / q, qq = ho % q, w = wo / r, rr = wo % r;
+    const long long vin = (((long long)n * T + t) * H + h) * W + w;
+    const int sub = (pp * q + qq) * r + rr;
+    __nv_bfloat16* yp = y + ((((long long)n * T * p + to) * (H * q) + ho) * (long long)(W * r) + wo) * c + v8 * 8;
+    const long long xb = vin * ((long long)c * pqr) + (long long)(v8 * 8) * pqr + sub;
+    if (!inverse) {
+      __nv_bfloat16 tmp[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tmp[k] = x[xb + (long long)k * pqr];
+      *reinterpret_cast<uint4*>(yp) = *reinterpret_cast<uint4*>(tmp);
+    } else {
+      // inverse: here `y` is the SHUFFLED tensor (read) and `x` the un-shuffled one (written)
+      __nv_bfloat16 tmp[8];
+      *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(yp);
+      __nv_bfloat16* xw = const_cast<__nv_bfloat16*>(x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xw[xb + (long long)k * pqr] = tmp[k];
+    }
+  }
+}
+
+// im2col: x NDHWC (bf16) -> col [M = N*To*Ho*Wo][kpad], k = tap*C + ci; zero for padding / OOB / k >= ntaps*C
+__global__ void og_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int T, int H,
+                                 int W, int C, int To, int Ho, int Wo, int kt, int kh, int kw, int st, int sh, int sw,
+                                 int pt, int ph, int pw, int kpad, long long total) {
+  const int K = kt * kh * kw * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kpad);
+    long long m = i / kpad;
+    __nv_bfloat16 val = __float2bfloat16_rn(0.f);
+    if (k < K) {
+      const int ci = k % C;
+      const int tap = k / C;
+      const int iw = tap % kw, ih = (tap / kw) % kh, it = tap / (kw * kh);
+      const int wo = (int)(m % Wo);
+      m /= Wo;
+      const int ho = (int)(m % Ho);
+      m /= Ho;
+      const int to = (int)(m % To);
+      const int n = (int)(m / To);
+      const int t = to * st + it - pt, h = ho * sh + ih - ph, w = wo * sw + iw - pw;
+      if (t >= 0 && t < T && h >= 0 && h < H && w >= 0 && w < W)
+        val = x[((((long long)n * T + t) * H + h) * W + w) * C + ci];
+    }
+    col[i] = val;
+  }
+}
+
+// col2im (gather form, deterministic): dx[n,t,h,w,ci] = sum over taps/outputs that read this input element
+template <typename OutT>
+__global__ void og_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, OutT* __restrict__ dx, int T, int H, int W,
+                                 int C, int To, int Ho, int Wo, int kt, int kh, int kw, int st, int sh, int sw, int pt,
+                                 int ph, int pw, int kpad, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C);
+    long long v = i / C;
+    const int w = (int)(v % W);
+    v /= W;
+    const int h = (int)(v % H);
+    v /= H;
+    const int t = (int)(v % T);
+    const int n = (int)(v / T);
+    float acc = 0.f;
+    for (int it = 0; it < kt; ++it) {
+      const int tn = t + pt - it;
+      if (tn < 0 || tn % st) continue;
+      const int to = tn / st;
+      if (to >= To) continue;
+      for (int ih = 0; ih < kh; ++ih) {
+        const int hn = h + ph - ih;
+        if (hn < 0 || hn % sh) continue;
+        const int ho = hn / sh;
+        if (ho >= Ho) continue;
+        for (int iw = 0; iw < kw; ++iw) {
+          const int wn = w + pw - iw;
+          if (wn < 0 || wn % sw) continue;
+          const int wo = wn / sw;
+          if (wo >= Wo) continue;
+          const long long m = (((long long)n * To + to) * Ho + ho) * Wo + wo;
+          const int tap = (it * kh + ih) * kw + iw;
+          acc += __bfloat162float(dcol[m * kpad + (long long)tap * C + ci]);
+        }
+      }
+    }
+    if constexpr (sizeof(OutT) == 2)
+      dx[i] = __float2bfloat16_rn(acc);
+    else
+      dx[i] = acc;
+  }
+}
+
+// mse: rec NDHWC fp32 [N,V,C] vs target NCDHW fp32 [N,C,V]. loss_sum += sum (rec - tgt)^2
+__global__ void og_mse_fwd_kernel(const float* __restrict__ rec, const float* __restrict__ tgt, int C, long long V,
+                                  long long total, float* __restrict__ loss_sum) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // iterate in target (NCDHW) order: i = (n*C + c)*V + v  -> coalesced target reads; rec reads are
+    // C-strided but C is tiny (3) so every sector is still fully used across the c-loop of neighbours
+    const long long v = i % V;
+    const long long nc = i / V;
+    const int c = (int)(nc % C);
+    const long long n = nc / C;
+    const float d = rec[(n * V + v) * C + c] - tgt[i];
+    acc = fmaf(d, d, acc);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float ws[32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+  }
+}
+
+// d_rec[n,v,c] = gscale * 2 (rec - tgt) / numel, written as bf16 NDHWC with cpad channels (zero padded)
+__global__ void og_mse_bwd_kernel(const float* __restrict__ rec, const float* __restrict__ tgt,
+                                  const float* __restrict__ gscale, float coef, int C, int cpad, long long V,
+                                  long long total, __nv_bfloat16* __restrict__ drec) {
+  const float g = (gscale ? *gscale : 1.f) * coef;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpad);
+    const long long nv = i / cpad;
+    float val = 0.f;
+    if (c < C) {
+      const long long n = nv / V, v = nv % V;
+      val = g * (rec[nv * C + c] - tgt[(n * C + c) * V + v]);
+    }
+    drec[i] = __float2bfloat16_rn(val);
+  }
+}
+
+// column sums (bias gradient): out[c] += sum_rows x[row][c]; x bf16 [rows][ld], first C columns
+__global__ void og_colsum_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, int ld,
+                                 float* __restrict__ out) {
+  // block handles 64 rows x all columns; thread t -> column t (loop), coalesced along c
+  const long long r0 = (long long)blockIdx.x * 256;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < 256; ++r) {
+      const long long row = r0 + r;
+      if (row >= rows) break;
+      acc += __bfloat162float(x[row * ld + c]);
+    }
+    atomicAdd(&out[c], acc);
+  }
+}
+
+// copy [rows][cs] -> [rows][cd] (cd >= cs zero padded, or cd < cs truncating); src f32 or bf16, dst bf16
+template <typename InT>
+__global__ void og_pad_channels_kernel(const InT* __restrict__ x, __nv_bfloat16* __restrict__ y, int cs, int cd,
+                                       long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cd);
+    const long long row = i / cd;
+    float v = 0.f;
+    if (c < cs) {
+      if constexpr (sizeof(InT) == 2)
+        v = __bfloat162float(x[row * cs + c]);
+      else
+        v = x[row * cs + c];
+    }
+    y[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// strided row copy with cast: dst[row*dst_ld + c] = bf16(src[row*src_ld + c]), c < cols
+template <typename InT>
+__global__ void og_copy_rows_kernel(const InT* __restrict__ src, long long src_ld, __nv_bfloat16* __restrict__ dst,
+                                    long long dst_ld, int cols, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long long row = i / cols;
+    float v;
+    if constexpr (sizeof(InT) == 2)
+      v = __bfloat162float(src[row * src_ld + c]);
+    else
+      v = src[row * src_ld + c];
+    dst[row * dst_ld + c] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace og
+
+using namespace og;
+
+extern "C" int og_copy_rows_to_bf16(const void* src, int src_f32, int64_t src_ld, void* dst, int64_t dst_ld,
+                                    int64_t rows, int cols, og_stream_t stream) {
+  OG_REQUIRE(src && dst && rows > 0 && cols > 0, "copy_rows_to_bf16: bad arguments");
+  const long long total = (long long)rows * cols;
+  if (src_f32)
+    og_copy_rows_kernel<float><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, cols, total);
+  else
+    og_copy_rows_kernel<__nv_bfloat16><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, src_ld, (__nv_bfloat16*)dst, dst_ld, cols, total);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_ncdhw_f32_to_ndhwc(const float* x, void* y, int y_f32, int N, int C, int64_t V,
+                                     og_stream_t stream) {
+  OG_REQUIRE(x && y && N > 0 && C > 0 && V > 0, "ncdhw_to_ndhwc: bad arguments");
+  dim3 grid((unsigned)((V + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  if (y_f32)
+    og_ncdhw_to_ndhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(x, (float*)y, C, V);
+  else
+    og_ncdhw_to_ndhwc_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, C, V);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_ndhwc_to_ncdhw_f32(const void* x, int x_f32, float* y, int N, int C, int64_t V,
+                                     og_stream_t stream) {
+  OG_REQUIRE(x && y && N > 0 && C > 0 && V > 0, "ndhwc_to_ncdhw: bad arguments");
+  dim3 grid((unsigned)((V + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  if (x_f32)
+    og_ndhwc_to_ncdhw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, y, C, V);
+  else
+    og_ndhwc_to_ncdhw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, C, V);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_pixel_shuffle3d(const void* x, void* y, int inverse, int N, int T, int H, int W, int c, int p,
+                                  int q, int r, og_stream_t stream) {
+  OG_REQUIRE(x && y, "pixel_shuffle3d: null pointer");
+  OG_REQUIRE(c % 8 == 0 && p >= 1 && q >= 1 && r >= 1, "pixel_shuffle3d: c=%d must be a multiple of 8", c);
+  const long long total = (long long)N * T * p * H * q * W * r * (c / 8);
+  // forward: x un-shuffled (read), y shuffled (written). inverse: y shuffled (read), x un-shuffled (written).
+  og_pixel_shuffle_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, T, H, W, c, p, q, r, total, inverse);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_im2col3d(const void* x, void* col, int N, int T, int H, int W, int C, int kt, int kh, int kw,
+                           int st, int sh, int sw, int pt, int ph, int pw, int kpad, og_stream_t stream) {
+  OG_REQUIRE(x && col, "im2col3d: null pointer");
+  OG_REQUIRE(kpad >= kt * kh * kw * C, "im2col3d: kpad=%d < %d", kpad, kt * kh * kw * C);
+  // causal "same" geometry of CausalConv3d (video.py:154-164): full front pad in time, symmetric in space
+  const int To = (T + pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+  const long long total = (long long)N * To * Ho * Wo * kpad;
+  og_im2col_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)col, T, H, W, C, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, kpad,
+      total);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_col2im3d(const void* dcol, void* dx, int dx_f32, int N, int T, int H, int W, int C, int kt, int kh,
+                           int kw, int st, int sh, int sw, int pt, int ph, int pw, int kpad, og_stream_t stream) {
+  OG_REQUIRE(dcol && dx, "col2im3d: null pointer");
+  const int To = (T + pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+  const long long total = (long long)N * T * H * W * C;
+  if (dx_f32)
+    og_col2im_kernel<float><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dcol, (float*)dx, T, H, W, C, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, kpad, total);
+  else
+    og_col2im_kernel<__nv_bfloat16><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, T, H, W, C, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw,
+        kpad, total);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_mse_fwd(const float* rec_ndhwc, const float* tgt_ncdhw, int N, int C, int64_t V, float* loss_sum,
+                          og_stream_t stream) {
+  OG_REQUIRE(rec_ndhwc && tgt_ncdhw && loss_sum, "mse_fwd: null pointer");
+  const long long total = (long long)N * C * V;
+  og_mse_fwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(rec_ndhwc, tgt_ncdhw, C, V, total,
+                                                                            loss_sum);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_mse_bwd(const float* rec_ndhwc, const float* tgt_ncdhw, const float* gscale, int N, int C, int cpad,
+                          int64_t V, void* drec, og_stream_t stream) {
+  OG_REQUIRE(rec_ndhwc && tgt_ncdhw && drec && cpad >= C, "mse_bwd: bad arguments");
+  const long long total = (long long)N * V * cpad;
+  const float coef = (float)(2.0 / ((double)N * C * V));
+  og_mse_bwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(rec_ndhwc, tgt_ncdhw, gscale, coef, C,
+                                                                            cpad, V, total, (__nv_bfloat16*)drec);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_colsum(const void* x, int64_t rows, int C, int ld, float* out, og_stream_t stream) {
+  OG_REQUIRE(x && out && C > 0 && ld >= C, "colsum: bad arguments");
+  const unsigned blocks = (unsigned)((rows + 255) / 256);
+  og_colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, ld, out);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_pad_channels(const void* x, int x_f32, void* y, int64_t rows, int cs, int cd, og_stream_t stream) {
+  OG_REQUIRE(x && y && cs > 0 && cd > 0, "pad_channels: bad arguments");
+  const long long total = (long long)rows * cd;
+  if (x_f32)
+    og_pad_channels_kernel<float><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x,
+                                                                                        (__nv_bfloat16*)y, cs, cd, total);
+  else
+    og_pad_channels_kernel<__nv_bfloat16><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, cs, cd, total);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}

@@ -1,0 +1,373 @@
+// norm_act.cu — GroupNorm / AdaptiveGroupNorm + activation on NDHWC bf16 tensors, forward and backward.
+//
+// These are HBM-bound passes (2+2 bytes per element), so the design is about traffic:
+//   * statistics: ONE read of x  -> per-(sample, group) sum / sum-of-squares (fp32 partials, fp64 combine)
+//   * apply     : one read + one write; the whole GN / AdaGN / affine / SiLU chain is folded into a
+//                 per-(sample, channel) scale A and shift B computed by a tiny finalize kernel:
+//                     y = act(x * A[n][c] + B[n][c])
+//                 A = rstd * gamma * s,  B = (beta - mean * rstd * gamma) * s + a        (s, a: AdaGN)
+//   * backward  : one reduce pass (dy, x) -> per-(n,c) sums, tiny finalize, one apply pass
+//                     dx = P[n][c] * dpre + Q[n][c] * x + R[n][c]  (+ add)
+//
+// Replaces F.group_norm / nn.GroupNorm + nn.SiLU (genie/module/video.py:607-608,622-623, blueprint
+// 'group_norm'+'silu' tokenizer.py:75-79,163-167), AdaptiveGroupNorm.forward (genie/module/norm.py:55-69)
+// and the GroupNorm of the ST-block FFN (genie/module/misc.py:93), plus their autograd backward.
+#include "og_host.cuh"
+#include "og_ptx.cuh"
+
+namespace og {
+extern std::atomic<uint64_t> g_launches;
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_grad_f(float x) {
+  const float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// statistics: grid (chunks, N); block 256. Thread -> (channel vector cv, row lane rl).
+// ------------------------------------------------------------------------------------------------
+static constexpr int kStatRows = 256;  // voxel rows per block
+
+__global__ void __launch_bounds__(256) og_gn_stats_kernel(const uint4* __restrict__ x, long long V, int C, int G,
+                                                          double* __restrict__ sums) {
+  const int cvs = C >> 3;  // channel vectors per row
+  const int n = blockIdx.y;
+  const long long row0 = (long long)blockIdx.x * kStatRows;
+  const int rows_per_pass = 256 / cvs > 0 ? 256 / cvs : 1;
+  __shared__ double sh[64 * 2];  // up to 64 groups
+  for (int i = threadIdx.x; i < 2 * G; i += 256) sh[i] = 0.0;
+  __syncthreads();
+  if (cvs <= 256) {
+    const int cv = threadIdx.x % cvs;
+    const int rl = threadIdx.x / cvs;
+    if (rl < rows_per_pass) {
+      float s = 0.f, ss = 0.f;
+      for (int r = rl; r < kStatRows; r += rows_per_pass) {
+        const long long row = row0 + r;
+        if (row >= V) break;
+        const uint4 u = __ldg(x + ((long long)n * V + row) * cvs + cv);
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s += f[i];
+          ss += f[i] * f[i];
+        }
+      }
+      const int g = (cv * 8) / (C / G);
+      atomicAdd(&sh[2 * g], (double)s);
+      atomicAdd(&sh[2 * g + 1], (double)ss);
+    }
+  } else {
+    for (int cv = threadIdx.x; cv < cvs; cv += 256) {
+      float s = 0.f, ss = 0.f;
+      for (int r = 0; r < kStatRows; ++r) {
+        const long long row = row0 + r;
+        if (row >= V) break;
+        const uint4 u = __ldg(x + ((long long)n * V + row) * cvs + cv);
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s += f[i];
+          ss += f[i] * f[i];
+        }
+      }
+      const int g = (cv * 8) / (C / G);
+      atomicAdd(&sh[2 * g], (double)s);
+      atomicAdd(&sh[2 * g + 1], (double)ss);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&sums[(long long)n * G * 2 + i], sh[i]);
+}
+
+// finalize: one thread per (n, c)
+__global__ void og_gn_finalize_kernel(const double* __restrict__ sums, int N, int C, int G, double inv_count, float eps,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ cond_scale, const float* __restrict__ cond_shift,
+                                      float* __restrict__ A, float* __restrict__ B, float* __restrict__ mean_rstd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * C) return;
+  const int n = idx / C, c = idx - n * C;
+  const int g = c / (C / G);
+  const double s = sums[((long long)n * G + g) * 2], ss = sums[((long long)n * G + g) * 2 + 1];
+  const double mean = s * inv_count;
+  double var = ss * inv_count - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float mu = (float)mean;
+  const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  float a = rstd * ga;
+  float b = be - mu * rstd * ga;
+  if (cond_scale) {
+    const float sc = cond_scale[idx];
+    a *= sc;
+    b *= sc;
+  }
+  if (cond_shift) b += cond_shift[idx];
+  A[idx] = a;
+  B[idx] = b;
+  if (c == g * (C / G)) {
+    mean_rstd[((long long)n * G + g) * 2] = mu;
+    mean_rstd[((long long)n * G + g) * 2 + 1] = rstd;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply: y = act(x*A + B). grid-stride over 8-channel vectors.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) og_affine_act_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ A,
+                                                                const float* __restrict__ B, uint4* __restrict__ y,
+                                                                long long V, int C, long long total_vec, int act) {
+  const int cvs = C >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvs);
+    const long long row = i / cvs;
+    const int n = (int)(row / V);
+    const float4* a4 = reinterpret_cast<const float4*>(A + (long long)n * C + cv * 8);
+    const float4* b4 = reinterpret_cast<const float4*>(B + (long long)n * C + cv * 8);
+    const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float f[8];
+    unpack8(__ldg(x + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float pre = fmaf(f[k], av[k], bv[k]);
+      f[k] = act ? silu_f(pre) : pre;
+    }
+    y[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward reduce: S[n][c] = (sum_v dpre, sum_v dpre * x), dpre = dy * act'(x*A+B)
+// grid (chunks, N), block 256; same thread mapping as the stats kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    og_affine_act_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                    const float* __restrict__ A, const float* __restrict__ B, long long V, int C,
+                                    int act, float* __restrict__ S) {
+  const int cvs = C >> 3;
+  const int n = blockIdx.y;
+  const long long row0 = (long long)blockIdx.x * kStatRows;
+  extern __shared__ float shs[];  // [C][2]
+  for (int i = threadIdx.x; i < 2 * C; i += 256) shs[i] = 0.f;
+  __syncthreads();
+  const int rows_per_pass = (cvs <= 256) ? 256 / cvs : 1;
+  for (int cv = threadIdx.x % (cvs < 256 ? cvs : 256); cv < cvs; cv += 256) {
+    const int rl = (cvs <= 256) ? threadIdx.x / cvs : 0;
+    if (rl >= rows_per_pass) break;
+    float av[8], bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      av[k] = A[(long long)n * C + cv * 8 + k];
+      bv[k] = B[(long long)n * C + cv * 8 + k];
+    }
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = rl; r < kStatRows; r += rows_per_pass) {
+      const long long row = row0 + r;
+      if (row >= V) break;
+      const long long i = ((long long)n * V + row) * cvs + cv;
+      float fx[8], fd[8];
+      unpack8(__ldg(x + i), fx);
+      unpack8(__ldg(dy + i), fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
+        s1[k] += dpre;
+        s2[k] = fmaf(dpre, fx[k], s2[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&shs[2 * (cv * 8 + k)], s1[k]);
+      atomicAdd(&shs[2 * (cv * 8 + k) + 1], s2[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&S[(long long)n * C * 2 + i], shs[i]);
+}
+
+// backward finalize: one block per sample n, 256 threads.
+//   T1 = S1, T2 = rstd*(S2 - mean*S1);  g' = gamma*s
+//   m1_g = sum_{c in g} g' T1 / M,  m2_g = sum_{c in g} g' T2 / M     (M = V * C/G)
+//   P = A,  Q = -rstd^2 m2,  R = rstd (m2 rstd mean - m1)
+//   dgamma[c] += s T2, dbeta[c] += s T1 (atomic over n), dscale[n][c] = gamma T2 + beta T1, dshift[n][c] = T1
+__global__ void __launch_bounds__(256)
+    og_gn_bwd_finalize_kernel(const float* __restrict__ S, const float* __restrict__ mean_rstd,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const float* __restrict__ cond_scale, int C, int G, double inv_M, float* __restrict__ Q,
+                              float* __restrict__ R, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                              float* __restrict__ dcond_scale, float* __restrict__ dcond_shift) {
+  const int n = blockIdx.x;
+  __shared__ double m1s[64], m2s[64];
+  for (int i = threadIdx.x; i < G; i += blockDim.x) m1s[i] = m2s[i] = 0.0;
+  __syncthreads();
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mu = mean_rstd[((long long)n * G + g) * 2], rstd = mean_rstd[((long long)n * G + g) * 2 + 1];
+    const float s1 = S[((long long)n * C + c) * 2], s2 = S[((long long)n * C + c) * 2 + 1];
+    const float t1 = s1, t2 = rstd * (s2 - mu * s1);
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float sc = cond_scale ? cond_scale[(long long)n * C + c] : 1.f;
+    const float gp = ga * sc;
+    atomicAdd(&m1s[g], (double)(gp * t1));
+    atomicAdd(&m2s[g], (double)(gp * t2));
+    if (dgamma) atomicAdd(&dgamma[c], sc * t2);
+    if (dbeta) atomicAdd(&dbeta[c], sc * t1);
+    if (dcond_scale) dcond_scale[(long long)n * C + c] = ga * t2 + be * t1;
+    if (dcond_shift) dcond_shift[(long long)n * C + c] = t1;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mu = mean_rstd[((long long)n * G + g) * 2], rstd = mean_rstd[((long long)n * G + g) * 2 + 1];
+    const float m1 = (float)(m1s[g] * inv_M), m2 = (float)(m2s[g] * inv_M);
+    Q[(long long)n * C + c] = -rstd * rstd * m2;
+    R[(long long)n * C + c] = rstd * (m2 * rstd * mu - m1);
+  }
+}
+
+// backward apply: dx = P*dpre + Q*x + R (+ add)
+__global__ void __launch_bounds__(256)
+    og_affine_act_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                   const float* __restrict__ A, const float* __restrict__ B,
+                                   const float* __restrict__ Q, const float* __restrict__ R,
+                                   const uint4* __restrict__ add, uint4* __restrict__ dx, long long V, int C,
+                                   long long total_vec, int act) {
+  const int cvs = C >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % cvs);
+    const long long row = i / cvs;
+    const int n = (int)(row / V);
+    const long long o = (long long)n * C + cv * 8;
+    float fx[8], fd[8], fa[8];
+    unpack8(__ldg(x + i), fx);
+    unpack8(__ldg(dy + i), fd);
+    if (add) unpack8(__ldg(add + i), fa);
+    float out[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a = __ldg(A + o + k), b = __ldg(B + o + k);
+      const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], a, b)) : fd[k];
+      float v = a * dpre;
+      if (Q) v += __ldg(Q + o + k) * fx[k] + __ldg(R + o + k);
+      if (add) v += fa[k];
+      out[k] = v;
+    }
+    dx[i] = pack8(out);
+  }
+}
+
+static int ew_grid(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace og
+
+using namespace og;
+
+extern "C" int og_gn_stats(const void* x, int N, int64_t V, int C, int G, double* sums, og_stream_t stream) {
+  OG_REQUIRE(x && sums, "gn_stats: null pointer");
+  OG_REQUIRE(C % 8 == 0 && G >= 1 && G <= 64 && C % G == 0 && (C / G) % 8 == 0,
+             "gn_stats: need C%%8==0, G<=64, (C/G)%%8==0 (C=%d G=%d)", C, G);
+  dim3 grid((unsigned)((V + kStatRows - 1) / kStatRows), N);
+  og_gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), V, C, G, sums);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_gn_finalize(const double* sums, int N, int C, int G, int64_t V, float eps, const float* gamma,
+                              const float* beta, const float* cond_scale, const float* cond_shift, float* A, float* B,
+                              float* mean_rstd, og_stream_t stream) {
+  OG_REQUIRE(sums && A && B && mean_rstd, "gn_finalize: null pointer");
+  const double inv_count = 1.0 / ((double)V * (C / G));
+  const int total = N * C;
+  og_gn_finalize_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      sums, N, C, G, inv_count, eps, gamma, beta, cond_scale, cond_shift, A, B, mean_rstd);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_affine_act_fwd(const void* x, const float* A, const float* B, void* y, int N, int64_t V, int C,
+                                 int act, og_stream_t stream) {
+  OG_REQUIRE(x && A && B && y, "affine_act_fwd: null pointer");
+  OG_REQUIRE(C % 8 == 0, "affine_act_fwd: C=%d must be a multiple of 8", C);
+  const long long total = (long long)N * V * (C / 8);
+  og_affine_act_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), A, B, reinterpret_cast<uint4*>(y), V, C, total, act);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_affine_act_bwd_reduce(const void* dy, const void* x, const float* A, const float* B, int act,
+                                        float* S, int N, int64_t V, int C, og_stream_t stream) {
+  OG_REQUIRE(dy && x && A && B && S, "affine_act_bwd_reduce: null pointer");
+  OG_REQUIRE(C % 8 == 0 && C <= 4096, "affine_act_bwd_reduce: C=%d must be a multiple of 8 and <= 4096", C);
+  dim3 grid((unsigned)((V + kStatRows - 1) / kStatRows), N);
+  og_affine_act_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, V, C, act, S);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_gn_bwd_finalize(const float* S, const float* mean_rstd, const float* gamma, const float* beta,
+                                  const float* cond_scale, int N, int C, int G, int64_t V, float* Q, float* R,
+                                  float* dgamma, float* dbeta, float* dcond_scale, float* dcond_shift,
+                                  og_stream_t stream) {
+  OG_REQUIRE(S && mean_rstd && Q && R, "gn_bwd_finalize: null pointer");
+  OG_REQUIRE(G <= 64, "gn_bwd_finalize: G=%d > 64", G);
+  const double inv_M = 1.0 / ((double)V * (C / G));
+  og_gn_bwd_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(S, mean_rstd, gamma, beta, cond_scale, C, G, inv_M, Q,
+                                                                 R, dgamma, dbeta, dcond_scale, dcond_shift);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_affine_act_bwd_apply(const void* dy, const void* x, const float* A, const float* B, const float* Q,
+                                       const float* R, const void* add, void* dx, int act, int N, int64_t V, int C,
+                                       og_stream_t stream) {
+  OG_REQUIRE(dy && x && A && B && dx, "affine_act_bwd_apply: null pointer");
+  OG_REQUIRE((Q == nullptr) == (R == nullptr), "affine_act_bwd_apply: Q and R must both be given or both NULL");
+  OG_REQUIRE(C % 8 == 0, "affine_act_bwd_apply: C=%d must be a multiple of 8", C);
+  const long long total = (long long)N * V * (C / 8);
+  og_affine_act_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, Q, R,
+      reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), V, C, total, act);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}

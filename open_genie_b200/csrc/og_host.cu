@@ -71,25 +71,27 @@ int num_sms() {
   return n;
 }
 
-bool choose_voxel_box(int vox, int T, int H, int W, int* bw, int* bh, int* bt) {
-  // widest-first: fill W, then H, then T with power-of-two factors of `vox`
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p *= 2;
+  return p;
+}
+
+void choose_voxel_box(int vox, int N, int T, int H, int W, int* bw, int* bh, int* bt, int* bn) {
   int rem = vox;
-  int w = 1;
-  while (w * 2 <= rem && W % (w * 2) == 0) w *= 2;
+  int w = pow2_ceil(W) < rem ? pow2_ceil(W) : rem;
   rem /= w;
-  int h = 1;
-  while (h * 2 <= rem && H % (h * 2) == 0) h *= 2;
+  int h = pow2_ceil(H) < rem ? pow2_ceil(H) : rem;
   rem /= h;
-  int t = 1;
-  while (t * 2 <= rem && T % (t * 2) == 0) t *= 2;
+  int t = pow2_ceil(T) < rem ? pow2_ceil(T) : rem;
   rem /= t;
-  if (rem != 1) return false;
-  // a box that is narrower than W must still tile H/T exactly (guaranteed by the divisibility loop)
-  if (w > 256 || h > 256 || t > 256) return false;
+  int n = rem;  // whatever is left spans samples
+  if (n > 256) n = 256;
   *bw = w;
   *bh = h;
   *bt = t;
-  return true;
+  *bn = n;
+  (void)N;
 }
 
 }  // namespace og

@@ -46,9 +46,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 int num_sms();
 
-// Decompose a block of `vox` (power of two) output voxels into a (bw, bh, bt) box over (W, H, T).
-// Returns false when the shape cannot be tiled (dims must be divisible by the chosen box).
-bool choose_voxel_box(int vox, int T, int H, int W, int* bw, int* bh, int* bt);
+// Decompose a block of `vox` (power of two) voxels into a (bw, bh, bt, bn) box over (W, H, T, N):
+// widest-first powers of two. Dimensions need not divide: partial boxes are zero-filled by TMA on
+// load and masked on store.
+void choose_voxel_box(int vox, int N, int T, int H, int W, int* bw, int* bh, int* bt, int* bn);
 
 static inline int ilog2(int v) {
   int l = 0;

@@ -1,0 +1,453 @@
+"""Autograd-aware Python bindings of the CUDA hot path (everything goes through the C ABI in _lib).
+
+Internal tensor convention ("internal format"): a video is a torch tensor with the reference's LOGICAL
+shape (B, C, T, H, W) whose memory is NDHWC (channels-last-3d) — bf16 between kernels, fp32 for the few
+tensors that feed a loss (encoder head -> LFQ, decoder tail -> mse). `to_internal` / `to_reference`
+convert at the public boundary (the reference is NCDHW fp32 everywhere, e.g. genie/tokenizer.py:307-330).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'open_genie_b200: {what} must be a CUDA tensor — this package has no CPU path '
+                           f'(the CPU restatement lives in oracle/ and is test infrastructure only)')
+
+
+def empty_internal(B: int, C: int, T: int, H: int, W: int, dtype=bf16, device='cuda') -> Tensor:
+    """Logical (B,C,T,H,W), physical NDHWC."""
+    return torch.empty((B, T, H, W, C), dtype=dtype, device=device).permute(0, 4, 1, 2, 3)
+
+
+def is_internal(x: Tensor) -> bool:
+    return x.dim() == 5 and x.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def to_internal(x: Tensor, dtype=bf16) -> Tensor:
+    """Reference-format tensor (any layout / float dtype) -> internal format of `dtype` (no autograd)."""
+    _require_cuda(x, 'input')
+    if x.dim() != 5:
+        raise ValueError(f'expected a 5-D (B,C,T,H,W) tensor, got shape {tuple(x.shape)}')
+    if is_internal(x) and x.dtype == dtype:
+        return x
+    B, C, T, H, W = x.shape
+    if is_internal(x):  # only the dtype differs: row copy with cast
+        y = empty_internal(B, C, T, H, W, dtype, x.device)
+        if dtype == bf16:
+            _lib.call('og_copy_rows_to_bf16', x.data_ptr(), int(x.dtype == f32), C, y.data_ptr(), C, B * T * H * W, C,
+                      _stream())
+            return y
+        return x.permute(0, 2, 3, 4, 1).to(dtype).permute(0, 4, 1, 2, 3)
+    xs = x.detach()
+    if xs.dtype != f32 or not xs.is_contiguous():
+        xs = xs.to(f32).contiguous()
+    y = empty_internal(B, C, T, H, W, dtype, x.device)
+    _lib.call('og_ncdhw_f32_to_ndhwc', xs.data_ptr(), y.data_ptr(), int(dtype == f32), B, C, T * H * W, _stream())
+    return y
+
+
+def to_reference(x: Tensor) -> Tensor:
+    """Internal-format tensor -> contiguous NCDHW fp32 (what the reference's public methods return)."""
+    if not is_internal(x) or x.dtype not in (bf16, f32):
+        return x.float().contiguous()
+    B, C, T, H, W = x.shape
+    y = torch.empty((B, C, T, H, W), dtype=f32, device=x.device)
+    _lib.call('og_ndhwc_to_ncdhw_f32', x.data_ptr(), int(x.dtype == f32), y.data_ptr(), B, C, T * H * W, _stream())
+    return y
+
+
+def _padded_ld(t: Tensor) -> int:
+    """Row pitch if `t` is a channel-slice [:, :C] of a wider internal bf16 tensor (as produced by
+    og_mse_bwd / og_lfq_bwd, whose pad channels are written as zeros), else 0."""
+    if t.dim() != 5 or t.dtype != bf16 or t.stride(1) != 1:
+        return 0
+    B, C, T, H, W = t.shape
+    cp = t.stride(4)
+    if cp >= C and t.stride(3) == W * cp and t.stride(2) == H * W * cp and t.stride(0) == T * H * W * cp:
+        return cp
+    return 0
+
+
+def _as_bf16_rows(t: Tensor, C: int, cpad: int) -> Tensor:
+    """Any gradient tensor of logical (B,C,T,H,W) -> bf16 internal rows [B*V][cpad] (zero padded)."""
+    if cpad != C and _padded_ld(t) == cpad:
+        return t                      # already a zero-padded row buffer: use its storage in place
+    if not is_internal(t):
+        t = to_internal(t, bf16)
+    if t.dtype == bf16 and cpad == C:
+        return t
+    B, _, T, H, W = t.shape
+    y = empty_internal(B, cpad, T, H, W, bf16, t.device)
+    if t.dtype not in (bf16, f32):
+        t = t.float()
+    _lib.call('og_pad_channels', t.data_ptr(), int(t.dtype == f32), y.data_ptr(), B * T * H * W, C, cpad, _stream())
+    return y
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+class ConvGeom:
+    """Static description of one conv layer (kernel, stride, causal/symmetric padding)."""
+
+    def __init__(self, cin, cout, kernel, stride=(1, 1, 1), pad_t_front=None, causal=True):
+        self.cin, self.cout = cin, cout
+        self.kt, self.kh, self.kw = kernel
+        self.st, self.sh, self.sw = stride
+        self.ph, self.pw = (self.kh - 1) // 2, (self.kw - 1) // 2
+        if pad_t_front is None:
+            # CausalConv3d: (kt-1)*dil + (1 - stride_t)  (genie/module/video.py:155); symmetric conv: (kt-1)//2
+            pad_t_front = (self.kt - 1) + (1 - self.st) if causal else (self.kt - 1) // 2
+        self.pt = pad_t_front
+        self.causal = causal
+        self.ntaps = self.kt * self.kh * self.kw
+        self.strided = stride != (1, 1, 1)
+        # implicit-GEMM kernel: stride 1, Cin multiple of 64; everything else goes through explicit im2col
+        self.direct = (not self.strided) and cin % 64 == 0
+        self.k_main = self.ntaps * cin
+        self.kpad = self.k_main if self.direct else _round_up(self.k_main, 64)
+        if not self.direct and not causal:
+            raise NotImplementedError('the im2col path implements CausalConv3d geometry only')
+
+    def out_dims(self, T, H, W):
+        if self.direct:
+            return T, H, W
+        return ((T + self.pt - self.kt) // self.st + 1, (H + 2 * self.ph - self.kh) // self.sh + 1,
+                (W + 2 * self.pw - self.kw) // self.sw + 1)
+
+
+def pack_weight(weight: Tensor, dst: Tensor, col_off: int):
+    """fp32 (Cout,Cin,kt,kh,kw) parameter (channels_last_3d memory = [Cout][tap][Cin]) -> bf16 segment of the
+    packed operand matrix dst[Cout][ld] starting at column col_off."""
+    w = weight.detach()
+    cout = w.shape[0]
+    k = w.numel() // cout
+    if not w.permute(0, 2, 3, 4, 1).is_contiguous():
+        w = w.permute(0, 2, 3, 4, 1).contiguous()
+    _lib.call('og_copy_rows_to_bf16', w.data_ptr(), 1, k, dst.data_ptr() + 2 * col_off, dst.shape[1], cout, k, _stream())
+
+
+class _Conv3dFn(torch.autograd.Function):
+    """y = conv(x; w, b) [+ conv1x1(x2; w2, b2)]   — og_conv3d_fwd / dgrad / wgrad, or im2col + the same kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, x2, weight2, bias2, packed, geom: ConvGeom, out_f32: bool):
+        _require_cuda(x, 'conv input')
+        B, C, T, H, W = x.shape
+        assert C == geom.cin, f'conv: expected {geom.cin} input channels, got {C}'
+        s = _stream()
+        xi = to_internal(x, bf16)
+        To, Ho, Wo = geom.out_dims(T, H, W)
+        y = empty_internal(B, geom.cout, To, Ho, Wo, f32 if out_f32 else bf16, x.device)
+        ldw = packed.shape[1]
+        x2i = None
+        col = None
+        if geom.direct:
+            c1 = 0
+            if x2 is not None:
+                x2i = to_internal(x2, bf16)
+                c1 = x2i.shape[1]
+            _lib.call('og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
+                      _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), y.data_ptr(), int(out_f32),
+                      B, T, H, W, geom.cout, s)
+        else:
+            assert x2 is None
+            col = torch.empty((B * To * Ho * Wo, geom.kpad), dtype=bf16, device=x.device)
+            _lib.call('og_im2col3d', xi.data_ptr(), col.data_ptr(), B, T, H, W, C, geom.kt, geom.kh, geom.kw,
+                      geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
+            _lib.call('og_conv3d_fwd', col.data_ptr(), geom.kpad, 1, 1, 1, 0, 0, 0, None, 0, packed.data_ptr(), ldw,
+                      _ptr(bias), None, y.data_ptr(), int(out_f32), 1, 1, 1, B * To * Ho * Wo, geom.cout, s)
+        ctx.geom = geom
+        ctx.in_shape = (B, C, T, H, W)
+        ctx.has_bias = (bias is not None, bias2 is not None)
+        ctx.w_shapes = (weight.shape, None if weight2 is None else weight2.shape)
+        ctx.save_for_backward(xi if geom.direct else col, x2i, packed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        geom: ConvGeom = ctx.geom
+        xs, x2i, packed = ctx.saved_tensors
+        B, C, T, H, W = ctx.in_shape
+        To, Ho, Wo = geom.out_dims(T, H, W)
+        s = _stream()
+        ldw = packed.shape[1]
+        cout = geom.cout
+        cpad = _round_up(cout, 64)
+        dyb = _as_bf16_rows(dy, cout, cpad)          # [B,To,Ho,Wo,cpad] bf16
+        need = ctx.needs_input_grad
+        dx = dw = db = dx2 = dw2 = db2 = None
+        dev = dy.device
+
+        def wgrad(xin, cin, kt, kh, kw, pt, ph, pw, shape5, dims):
+            """fp32 gradient with the parameter's channels_last_3d memory: [cout][tap][cin]."""
+            rows = cpad if cpad != cout else cout
+            g = torch.zeros((rows, kt * kh * kw * cin), dtype=f32, device=dev)
+            _lib.call('og_conv3d_wgrad', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(), g.shape[1],
+                      kt, kh, kw, pt, ph, pw, dims[0], dims[1], dims[2], dims[3], s)
+            return g[:cout]
+
+        if geom.direct:
+            if need[0]:
+                dx = empty_internal(B, C, T, H, W, bf16, dev)
+                _lib.call('og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, geom.kt, geom.kh,
+                          geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, s)
+            if need[1]:
+                g = wgrad(xs, C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, ctx.w_shapes[0], (B, T, H, W))
+                dw = g.view(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
+            if x2i is not None:
+                c1 = x2i.shape[1]
+                if need[3]:
+                    dx2 = empty_internal(B, c1, T, H, W, bf16, dev)
+                    _lib.call('og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, geom.k_main,
+                              1, 1, 1, 0, 0, 0, dx2.data_ptr(), 0, B, T, H, W, c1, s)
+                if need[4]:
+                    g = wgrad(x2i, c1, 1, 1, 1, 0, 0, 0, ctx.w_shapes[1], (B, T, H, W))
+                    dw2 = g.view(cout, 1, 1, 1, c1).permute(0, 4, 1, 2, 3)
+        else:
+            col = xs
+            if need[0]:
+                dcol = torch.empty_like(col)
+                _lib.call('og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, 1, 1, 1, 0, 0, 0,
+                          dcol.data_ptr(), 0, 1, 1, 1, B * To * Ho * Wo, geom.kpad, s)
+                dx = empty_internal(B, C, T, H, W, bf16, dev)
+                _lib.call('og_col2im3d', dcol.data_ptr(), dx.data_ptr(), 0, B, T, H, W, C, geom.kt, geom.kh, geom.kw,
+                          geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
+            if need[1]:
+                g = wgrad(col, geom.kpad, 1, 1, 1, 0, 0, 0, ctx.w_shapes[0], (1, 1, 1, B * To * Ho * Wo))
+                dw = g[:, :geom.k_main].reshape(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
+        if (ctx.has_bias[0] and need[2]) or (ctx.has_bias[1] and need[5]):
+            dbs = torch.zeros(cout, dtype=f32, device=dev)
+            _lib.call('og_colsum', dyb.data_ptr(), B * To * Ho * Wo, cout, cpad, dbs.data_ptr(), s)
+            if ctx.has_bias[0] and need[2]:
+                db = dbs
+            if ctx.has_bias[1] and need[5]:
+                db2 = dbs if db is None else dbs.clone()
+        return dx, dw, db, dx2, dw2, db2, None, None, None
+
+
+def conv3d(x, weight, bias, packed, geom, out_f32=False, x2=None, weight2=None, bias2=None):
+    return _Conv3dFn.apply(x, weight, bias, x2, weight2, bias2, packed, geom, out_f32)
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm / AdaGN (+ SiLU)
+# ------------------------------------------------------------------------------------------------
+class _GroupNormActFn(torch.autograd.Function):
+    """y = act(GN_G(x; gamma, beta) * cond_scale + cond_shift)"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, cond_scale, cond_shift, G: int, eps: float, act: int):
+        _require_cuda(x, 'group_norm input')
+        xi = to_internal(x, bf16)
+        B, C, T, H, W = xi.shape
+        V = T * H * W
+        s = _stream()
+        dev = xi.device
+        sums = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+        _lib.call('og_gn_stats', xi.data_ptr(), B, V, C, G, sums.data_ptr(), s)
+        A = torch.empty((B, C), dtype=f32, device=dev)
+        Bc = torch.empty((B, C), dtype=f32, device=dev)
+        mr = torch.empty((B, G, 2), dtype=f32, device=dev)
+        cs = None if cond_scale is None else cond_scale.detach().to(f32).contiguous()
+        csh = None if cond_shift is None else cond_shift.detach().to(f32).contiguous()
+        _lib.call('og_gn_finalize', sums.data_ptr(), B, C, G, V, eps, _ptr(gamma), _ptr(beta), _ptr(cs), _ptr(csh),
+                  A.data_ptr(), Bc.data_ptr(), mr.data_ptr(), s)
+        y = empty_internal(B, C, T, H, W, bf16, dev)
+        _lib.call('og_affine_act_fwd', xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), y.data_ptr(), B, V, C, act, s)
+        ctx.cfg = (G, act, cond_scale is not None, cond_shift is not None)
+        ctx.save_for_backward(xi, A, Bc, mr, gamma, beta, cs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xi, A, Bc, mr, gamma, beta, cs = ctx.saved_tensors
+        G, act, has_cs, has_csh = ctx.cfg
+        B, C, T, H, W = xi.shape
+        V = T * H * W
+        s = _stream()
+        dev = xi.device
+        dyb = _as_bf16_rows(dy, C, C)
+        S = torch.zeros((B, C, 2), dtype=f32, device=dev)
+        _lib.call('og_affine_act_bwd_reduce', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), act,
+                  S.data_ptr(), B, V, C, s)
+        Q = torch.empty((B, C), dtype=f32, device=dev)
+        R = torch.empty((B, C), dtype=f32, device=dev)
+        dgamma = torch.zeros(C, dtype=f32, device=dev) if gamma is not None else None
+        dbeta = torch.zeros(C, dtype=f32, device=dev) if beta is not None else None
+        dcs = torch.empty((B, C), dtype=f32, device=dev) if has_cs else None
+        dcsh = torch.empty((B, C), dtype=f32, device=dev) if has_csh else None
+        _lib.call('og_gn_bwd_finalize', S.data_ptr(), mr.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(cs), B, C, G, V,
+                  Q.data_ptr(), R.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(dcs), _ptr(dcsh), s)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_internal(B, C, T, H, W, bf16, dev)
+            _lib.call('og_affine_act_bwd_apply', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(),
+                      Q.data_ptr(), R.data_ptr(), None, dx.data_ptr(), act, B, V, C, s)
+        return dx, dgamma, dbeta, dcs, dcsh, None, None, None
+
+
+def group_norm_act(x, gamma, beta, num_groups, eps=1e-5, act='none', cond_scale=None, cond_shift=None):
+    return _GroupNormActFn.apply(x, gamma, beta, cond_scale, cond_shift, num_groups, eps, 1 if act == 'silu' else 0)
+
+
+class _ActFn(torch.autograd.Function):
+    """Stand-alone SiLU (blueprint entry 'silu', genie/tokenizer.py:79,167): y = silu(x)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xi = to_internal(x, bf16)
+        B, C, T, H, W = xi.shape
+        dev = xi.device
+        A = torch.ones((B, C), dtype=f32, device=dev)
+        Bc = torch.zeros((B, C), dtype=f32, device=dev)
+        y = empty_internal(B, C, T, H, W, bf16, dev)
+        _lib.call('og_affine_act_fwd', xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), y.data_ptr(), B, T * H * W, C, 1,
+                  _stream())
+        ctx.save_for_backward(xi, A, Bc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xi, A, Bc = ctx.saved_tensors
+        B, C, T, H, W = xi.shape
+        dyb = _as_bf16_rows(dy, C, C)
+        dx = empty_internal(B, C, T, H, W, bf16, xi.device)
+        _lib.call('og_affine_act_bwd_apply', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), None, None,
+                  None, dx.data_ptr(), 1, B, T * H * W, C, _stream())
+        return dx
+
+
+def silu(x):
+    return _ActFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# pixel shuffle (depth -> space-time)
+# ------------------------------------------------------------------------------------------------
+class _PixelShuffleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p: int, q: int, r: int):
+        xi = to_internal(x, bf16)
+        B, CC, T, H, W = xi.shape
+        c = CC // (p * q * r)
+        y = empty_internal(B, c, T * p, H * q, W * r, bf16, xi.device)
+        _lib.call('og_pixel_shuffle3d', xi.data_ptr(), y.data_ptr(), 0, B, T, H, W, c, p, q, r, _stream())
+        ctx.cfg = (B, CC, T, H, W, c, p, q, r)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, CC, T, H, W, c, p, q, r = ctx.cfg
+        dyb = _as_bf16_rows(dy, c, c)
+        dx = empty_internal(B, CC, T, H, W, bf16, dy.device)
+        _lib.call('og_pixel_shuffle3d', dx.data_ptr(), dyb.data_ptr(), 1, B, T, H, W, c, p, q, r, _stream())
+        return dx, None, None, None
+
+
+def pixel_shuffle3d(x, p, q, r):
+    return _PixelShuffleFn.apply(x, p, q, r)
+
+
+# ------------------------------------------------------------------------------------------------
+# mse loss between an internal fp32 reconstruction and the reference-format target
+# ------------------------------------------------------------------------------------------------
+class _MseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rec, target):
+        assert is_internal(rec) and rec.dtype == f32, 'mse: reconstruction must be internal fp32'
+        B, C, T, H, W = rec.shape
+        tgt = target.detach()
+        if tgt.dtype != f32 or not tgt.is_contiguous():
+            tgt = tgt.to(f32).contiguous()
+        acc = torch.zeros((), dtype=f32, device=rec.device)
+        _lib.call('og_mse_fwd', rec.data_ptr(), tgt.data_ptr(), B, C, T * H * W, acc.data_ptr(), _stream())
+        ctx.save_for_backward(rec, tgt)
+        return acc / float(rec.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        rec, tgt = ctx.saved_tensors
+        B, C, T, H, W = rec.shape
+        cpad = _round_up(C, 64)
+        gs = g.detach().to(f32).contiguous()
+        drec = empty_internal(B, cpad, T, H, W, bf16, rec.device)
+        _lib.call('og_mse_bwd', rec.data_ptr(), tgt.data_ptr(), gs.data_ptr(), B, C, cpad, T * H * W, drec.data_ptr(),
+                  _stream())
+        return drec[:, :C], None
+
+
+def mse_loss(rec, target):
+    return _MseFn.apply(rec, target)
+
+
+# ------------------------------------------------------------------------------------------------
+# Lookup-free quantisation
+# ------------------------------------------------------------------------------------------------
+class _LfqFn(torch.autograd.Function):
+    """x: fp32 [ntok, D] -> (out fp32 [ntok, D], idx int64 [ntok], loss scalar or None)."""
+
+    @staticmethod
+    def forward(ctx, x, D, beta, training, w_commit, w_entropy, w_div):
+        _require_cuda(x, 'lfq input')
+        xs = x.detach()
+        if xs.dtype != f32 or not xs.is_contiguous():
+            xs = xs.to(f32).contiguous()
+        ntok = xs.shape[0]
+        dev = xs.device
+        out = torch.empty((ntok, D), dtype=f32, device=dev)
+        idx = torch.empty((ntok,), dtype=torch.int64, device=dev)
+        loss = torch.zeros((), dtype=f32, device=dev)
+        ws = None
+        if training:
+            nbytes = _lib.load().og_lfq_workspace_bytes(ntok, D)
+            if nbytes == 0:
+                raise RuntimeError(f'lfq: codebook_dim={D} is outside the supported range [1, 20]')
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        _lib.call('og_lfq_fwd', xs.data_ptr(), xs.shape[1], ntok, D, beta, int(training), w_commit, w_entropy, w_div,
+                  out.data_ptr(), None, 0, idx.data_ptr(), loss.data_ptr(), _ptr(ws), _stream())
+        ctx.cfg = (D, beta, w_commit, w_entropy, training)
+        ctx.save_for_backward(xs, ws)
+        ctx.mark_non_differentiable(idx)
+        return out, idx, loss
+
+    @staticmethod
+    def backward(ctx, dout, _didx, dloss):
+        D, beta, w_commit, w_entropy, training = ctx.cfg
+        xs, ws = ctx.saved_tensors
+        if not training:
+            return (None,) * 7     # eval: code = sign(x) has no gradient path (quantization.py:101)
+        ntok = xs.shape[0]
+        dx = torch.empty((ntok, D), dtype=f32, device=xs.device)
+        do = None if dout is None else dout.detach().to(f32).contiguous()
+        gl = dloss.detach().to(f32).contiguous() if dloss is not None else torch.zeros((), device=xs.device)
+        _lib.call('og_lfq_bwd', xs.data_ptr(), xs.shape[1], ntok, D, beta, w_commit, w_entropy, gl.data_ptr(),
+                  _ptr(do), D, dx.data_ptr(), None, D, ws.data_ptr(), _stream())
+        return dx, None, None, None, None, None, None
+
+
+def lfq(x2d, D, beta, training, w_commit, w_entropy, w_div):
+    return _LfqFn.apply(x2d, D, float(beta), bool(training), float(w_commit), float(w_entropy), float(w_div))

@@ -1,0 +1,113 @@
+"""FusedAdamW — torch.optim.AdamW semantics (the reference's default optimizer, genie/tokenizer.py:250,437-442)
+as ONE multi-tensor CUDA launch per step (csrc/optim.cu), which also refreshes the bf16 operand copies the
+conv kernels read so no separate weight-cast pass exists."""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, Optional
+
+import torch
+from torch.optim import Optimizer
+
+from . import _lib
+
+
+class FusedAdamW(Optimizer):
+    def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, bf16_targets: Optional[dict] = None):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._step = 0
+        self._cache_key = None
+        self._size_key = None
+        self._dev_table = self._dev_ct = self._dev_ci = None
+        self._num_chunks = 0
+        self.grad_scale: Optional[torch.Tensor] = None   # device scalar multiplied into every gradient
+
+    def _bf16_target(self, p):
+        """Packed bf16 operand (tensor, column offset) of the conv that owns parameter p, if any."""
+        from .module.video import CONV_REGISTRY
+        m = CONV_REGISTRY.get(id(p))
+        if m is None or m.weight is not p:
+            return None
+        return m.bf16_target()
+
+    @staticmethod
+    def _dense_like(p: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+        """Gradient with exactly the parameter's memory order (elementwise kernel works on raw storage)."""
+        if g.dtype != torch.float32:
+            g = g.float()
+        if g.stride() == p.stride():
+            return g
+        out = torch.empty_like(p)          # preserves p's strides
+        out.copy_(g)
+        return out
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        entries = []
+        for group in self.param_groups:
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise RuntimeError('FusedAdamW: parameters must live on a CUDA device (no CPU path)')
+                st = self.state[p]
+                if not st:
+                    st['exp_avg'] = torch.zeros_like(p)      # same strides as p
+                    st['exp_avg_sq'] = torch.zeros_like(p)
+                g = self._dense_like(p, p.grad)
+                if g is not p.grad:
+                    p.grad = g
+                entries.append((p, g, st['exp_avg'], st['exp_avg_sq'], group))
+        if not entries:
+            return loss
+        self._step += 1
+        # one launch per param group (hyper-parameters are launch arguments)
+        by_group = {}
+        for e in entries:
+            by_group.setdefault(id(e[4]), []).append(e)
+        for ents in by_group.values():
+            self._launch(ents)
+        return loss
+
+    def _launch(self, ents):
+        group = ents[0][4]
+        chunk = _lib.load().og_adamw_chunk_elems()
+        key = tuple((p.data_ptr(), g.data_ptr()) for p, g, _, _, _ in ents) + tuple(
+            (t[0].data_ptr() if t else 0) for t in (self._bf16_target(p) for p, _, _, _, _ in ents))
+        if key != self._cache_key or len(self.param_groups) > 1:
+            n = len(ents)
+            table = (_lib.og_adamw_tensor * n)()
+            dev = ents[0][0].device
+            size_key = tuple(p.numel() for p, _, _, _, _ in ents)
+            if size_key != self._size_key:          # chunk map depends on sizes only: built once
+                import numpy as np
+                nchs = [(s + chunk - 1) // chunk for s in size_key]
+                ct = np.repeat(np.arange(n, dtype=np.int32), nchs)
+                ci = np.concatenate([np.arange(c, dtype=np.int32) for c in nchs])
+                self._dev_ct = torch.from_numpy(ct).pin_memory().to(dev, non_blocking=True)
+                self._dev_ci = torch.from_numpy(ci).pin_memory().to(dev, non_blocking=True)
+                self._num_chunks = int(ct.shape[0])
+                self._size_key = size_key
+            for i, (p, g, m, v, _) in enumerate(ents):
+                t = table[i]
+                t.p, t.g, t.m, t.v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+                t.n = p.numel()
+                tgt = self._bf16_target(p)
+                if tgt is not None:
+                    packed, col_off = tgt
+                    t.p_bf16 = packed.data_ptr() + 2 * col_off
+                    t.row_len = p.numel() // p.shape[0]
+                    t.dst_ld = packed.shape[1]
+                else:
+                    t.p_bf16, t.row_len, t.dst_ld = None, 1, 1
+            raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).pin_memory()
+            self._dev_table = raw.to(dev, non_blocking=True)
+            self._cache_key = key
+        b1, b2 = group['betas']
+        _lib.call('og_adamw_step', self._dev_table.data_ptr(), self._dev_ct.data_ptr(), self._dev_ci.data_ptr(),
+                  self._num_chunks, float(group['lr']), float(b1), float(b2), float(group['eps']),
+                  float(group['weight_decay']), self._step,
+                  None if self.grad_scale is None else self.grad_scale.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream)
