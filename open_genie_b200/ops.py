@@ -23,6 +23,22 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-launch timing of the tensor-core kernels (bench.py's roofline): when PROFILE is a list, every
+# conv launch appends (kind, flops, start_event, end_event). CUDA events on the launching stream; no syncs.
+PROFILE = None
+
+
+def _conv_call(kind: str, flops: float, name: str, *args):
+    if PROFILE is None:
+        return _lib.call(name, *args)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, *args)
+    e1.record()
+    PROFILE.append((kind, flops, e0, e1))
+
+
 def _ptr(t: Optional[Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -170,7 +186,8 @@ class _Conv3dFn(torch.autograd.Function):
             if x2 is not None:
                 x2i = to_internal(x2, bf16)
                 c1 = x2i.shape[1]
-            _lib.call('og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
+            _conv_call('fwd', 2.0 * B * T * H * W * geom.cout * (geom.k_main + c1),
+                       'og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
                       _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), y.data_ptr(), int(out_f32),
                       B, T, H, W, geom.cout, s)
         else:
@@ -178,7 +195,8 @@ class _Conv3dFn(torch.autograd.Function):
             col = torch.empty((B * To * Ho * Wo, geom.kpad), dtype=bf16, device=x.device)
             _lib.call('og_im2col3d', xi.data_ptr(), col.data_ptr(), B, T, H, W, C, geom.kt, geom.kh, geom.kw,
                       geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
-            _lib.call('og_conv3d_fwd', col.data_ptr(), geom.kpad, 1, 1, 1, 0, 0, 0, None, 0, packed.data_ptr(), ldw,
+            _conv_call('fwd', 2.0 * B * To * Ho * Wo * geom.cout * geom.k_main,
+                       'og_conv3d_fwd', col.data_ptr(), geom.kpad, 1, 1, 1, 0, 0, 0, None, 0, packed.data_ptr(), ldw,
                       _ptr(bias), None, y.data_ptr(), int(out_f32), 1, 1, 1, B * To * Ho * Wo, geom.cout, s)
         ctx.geom = geom
         ctx.in_shape = (B, C, T, H, W)
@@ -206,15 +224,17 @@ class _Conv3dFn(torch.autograd.Function):
             """fp32 gradient with the parameter's channels_last_3d memory: [cout][tap][cin]."""
             rows = cpad if cpad != cout else cout
             g = torch.zeros((rows, kt * kh * kw * cin), dtype=f32, device=dev)
-            _lib.call('og_conv3d_wgrad', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(), g.shape[1],
+            _conv_call('wgrad', 2.0 * dims[0] * dims[1] * dims[2] * dims[3] * cout * min(cin, geom.k_main) * kt * kh * kw,
+                       'og_conv3d_wgrad', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(), g.shape[1],
                       kt, kh, kw, pt, ph, pw, dims[0], dims[1], dims[2], dims[3], s)
             return g[:cout]
 
         if geom.direct:
             if need[0]:
                 dx = empty_internal(B, C, T, H, W, bf16, dev)
-                _lib.call('og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, geom.kt, geom.kh,
-                          geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, s)
+                _conv_call('dgrad', 2.0 * B * T * H * W * cout * geom.k_main,
+                           'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, geom.kt, geom.kh,
+                           geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, s)
             if need[1]:
                 g = wgrad(xs, C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, ctx.w_shapes[0], (B, T, H, W))
                 dw = g.view(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
@@ -222,8 +242,9 @@ class _Conv3dFn(torch.autograd.Function):
                 c1 = x2i.shape[1]
                 if need[3]:
                     dx2 = empty_internal(B, c1, T, H, W, bf16, dev)
-                    _lib.call('og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, geom.k_main,
-                              1, 1, 1, 0, 0, 0, dx2.data_ptr(), 0, B, T, H, W, c1, s)
+                    _conv_call('dgrad', 2.0 * B * T * H * W * cout * c1,
+                               'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, geom.k_main,
+                               1, 1, 1, 0, 0, 0, dx2.data_ptr(), 0, B, T, H, W, c1, s)
                 if need[4]:
                     g = wgrad(x2i, c1, 1, 1, 1, 0, 0, 0, ctx.w_shapes[1], (B, T, H, W))
                     dw2 = g.view(cout, 1, 1, 1, c1).permute(0, 4, 1, 2, 3)
@@ -231,8 +252,9 @@ class _Conv3dFn(torch.autograd.Function):
             col = xs
             if need[0]:
                 dcol = torch.empty_like(col)
-                _lib.call('og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, 1, 1, 1, 0, 0, 0,
-                          dcol.data_ptr(), 0, 1, 1, 1, B * To * Ho * Wo, geom.kpad, s)
+                _conv_call('dgrad', 2.0 * B * To * Ho * Wo * cout * geom.k_main,
+                           'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, 1, 1, 1, 0, 0, 0,
+                           dcol.data_ptr(), 0, 1, 1, 1, B * To * Ho * Wo, geom.kpad, s)
                 dx = empty_internal(B, C, T, H, W, bf16, dev)
                 _lib.call('og_col2im3d', dcol.data_ptr(), dx.data_ptr(), 0, B, T, H, W, C, geom.kt, geom.kh, geom.kw,
                           geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
