@@ -50,6 +50,7 @@ struct IgemmParams {
   const float* bias1;
   int num_stages;
   int num_kb;  // k-blocks per tile
+  int m_sub;   // M sub-tiles (of 128 rows) per CTA tile sharing one B stage: 1 or 2
 };
 
 static constexpr int kBlockM = 128;
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   // 1024-byte alignment: required by the 128-byte swizzle pattern shared by TMA and the UMMA descriptors
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
+  const int a_bytes = p.m_sub * kABytes;
+  const int stage_bytes = a_bytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_m_super = (p.num_m_tiles + p.m_sub - 1) / p.m_sub;
+  const int total_tiles = num_m_super * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -125,9 +128,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
-        const TileCoord tc = decode_m_tile(p, m_tile);
+        const int m_super = tile / p.num_n_tiles;
+        const int n_tile = tile - m_super * p.num_n_tiles;
+        const TileCoord tc = decode_m_tile(p, m_super * p.m_sub);
+        const TileCoord tc1 = decode_m_tile(p, m_super * p.m_sub + 1);  // second sub-tile (m_sub == 2)
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const IgemmSeg sg = p.seg[s];
@@ -142,9 +146,12 @@ __global__ void __launch_bounds__(kThreads, 1)
                 for (int cb = 0; cb < sg.cin_blocks; ++cb, ++kb) {
                   mbar_wait(&empty[stage], phase ^ 1);
                   uint8_t* sa = smem + stage * stage_bytes;
-                  uint8_t* sb = sa + kABytes;
+                  uint8_t* sb = sa + a_bytes;
                   mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
                   tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, cw, ch, ct, tc.n0);
+                  if (p.m_sub == 2)
+                    tma_load_5d(sa + kABytes, mapA, &full[stage], cb * kBlockK, tc1.w0 + p.sgn * (iw - sg.pw),
+                                tc1.h0 + p.sgn * (ih - sg.ph), tc1.t0 + p.sgn * (it - sg.pt), tc1.n0);
                   if (!p.b_mn_major) {
                     tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
                   } else {
@@ -179,19 +186,21 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t b_addr = a_addr + a_bytes;
+          for (int ms = 0; ms < p.m_sub; ++ms) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // A: K-major, 128-byte rows, 8-row groups 1024 B apart; advance 16 elements = 32 B inside the row
-            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            uint64_t bdesc;
-            if (!p.b_mn_major) {
-              bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            } else {
-              // B: MN-major panels [block_n/64][64 k-rows][128 B]; 16 k-rows = 2048 B; panel stride 8192 B
-              bdesc = umma_smem_desc_sw128(b_addr + k * 2048, 64 * 128, 1024);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // A: K-major, 128-byte rows, 8-row groups 1024 B apart; advance 16 elements = 32 B inside the row
+              const uint64_t adesc = umma_smem_desc_sw128(a_addr + ms * kABytes + k * 32, 16, 1024);
+              uint64_t bdesc;
+              if (!p.b_mn_major) {
+                bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              } else {
+                // B: MN-major panels [block_n/64][64 k-rows][128 B]; 16 k-rows = 2048 B; panel stride 8192 B
+                bdesc = umma_smem_desc_sw128(b_addr + k * 2048, 64 * 128, 1024);
+              }
+              umma_bf16_ss(d_tmem + ms * p.block_n, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == p.num_stages) {
@@ -212,9 +221,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
-      const TileCoord tc = decode_m_tile(p, m_tile);
+      const int m_super = tile / p.num_n_tiles;
+      const int n_tile = tile - m_super * p.num_n_tiles;
+      mbar_wait_relaxed(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      for (int ms = 0; ms < p.m_sub; ++ms) {
+      const TileCoord tc = decode_m_tile(p, m_super * p.m_sub + ms);
       const int dw = row & ((1 << p.bw_log2) - 1);
       const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
       const int dt = (row >> (p.bw_log2 + p.bh_log2)) & ((1 << p.bt_log2) - 1);
@@ -224,9 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const long long vox = (((long long)vn * p.T + vt) * p.H + vh) * p.W + vw;
       const int col0 = n_tile * p.block_n;
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * kAccStride + ms * p.block_n + ((uint32_t)(q * 32) << 16);
 
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t v[32];
@@ -282,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
+      }  // m_sub
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -355,7 +366,10 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   p.vec_ok = out_f32 ? (n_out % 4 == 0) : (n_out % 8 == 0);
   p.bias0 = bias0;
   p.bias1 = bias1;
-  const int stage_bytes = kABytes + p.block_n * kBlockK * 2;
+  // TMA latency x smem capacity bounds the bytes/clk one SM can stream; sharing each B stage between two
+  // 128-row M sub-tiles keeps the demand at (32+16) KB per 512 MMA-clk (same as a 128x256 tile).
+  p.m_sub = (p.block_n <= 128 && p.num_m_tiles >= 2 * num_sms()) ? 2 : 1;
+  const int stage_bytes = p.m_sub * kABytes + p.block_n * kBlockK * 2;
   int stages = (220 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
@@ -401,7 +415,7 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int total_tiles = ((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles;
   int grid = num_sms();
   if (grid > total_tiles) grid = total_tiles;
   og_conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapB, p);

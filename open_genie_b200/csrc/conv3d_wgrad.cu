@@ -13,6 +13,8 @@
 //
 // Replaces autograd's conv3d weight-gradient reached from genie/module/video.py:192,609-629,599-603 and
 // genie/module/attention.py:429-438 during loss.backward().
+#include <stdlib.h>
+
 #include "og_host.cuh"
 #include "og_ptx.cuh"
 
@@ -30,6 +32,8 @@ struct WgradParams {
   float* dw;
   long long ld_dw;
   int a_stages, b_stages;
+  int vec_ok;  // dw rows 16-byte aligned: vector reductions
+  int dbg;     // timing experiments only (OG_WGRAD_DBG): 1 = pretend A is K-major, 2 = pretend B is K-major, 4 = skip epilogue
 };
 
 static constexpr int kWThreads = 192;
@@ -43,7 +47,11 @@ __global__ void __launch_bounds__(kWThreads, 1)
                          const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = (p.block_n / 64) * kPanelBytes;
+  // One B stage holds a PAIR of taps back to back ([tap j panels][tap j+1 panels]); issued as a single
+  // UMMA of N = 2*block_n whose accumulator columns are the two taps' blocks. That halves the smem bytes
+  // the tensor core reads per MMA-clock for the A (dY) operand: 128x128 MMAs are smem-bandwidth bound.
+  const int tap_bytes = (p.block_n / 64) * kPanelBytes;
+  const int b_bytes = 2 * tap_bytes;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.a_stages * kWABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.b_stages * b_bytes);
@@ -58,8 +66,10 @@ __global__ void __launch_bounds__(kWThreads, 1)
   const int lane = threadIdx.x & 31;
   const int co0 = blockIdx.x * 128;
   const int ci0 = blockIdx.y * p.block_n;
-  const int group = blockIdx.z / p.splitk;
-  const int split = blockIdx.z - group * p.splitk;
+  // tap group is the FAST index: the CTAs that stream the same voxel range (same split, different taps)
+  // are co-scheduled, so dY / X tiles are fetched from DRAM once and hit in L2 for the other groups
+  const int split = blockIdx.z / p.num_groups;
+  const int group = blockIdx.z - split * p.num_groups;
   const int tap0 = group * p.taps_per_group;
   const int ntap = min(p.taps_per_group, p.ntaps - tap0);
   // contiguous k-step range of this split
@@ -90,14 +100,27 @@ __global__ void __launch_bounds__(kWThreads, 1)
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
+      // The producer is ONE thread: keep its per-k-step instruction count tiny (no divisions in the loop).
+      // tap offsets of this group, decoded once
+      int off_w[4], off_h[4], off_t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int tap = tap0 + (j < ntap ? j : 0);
+        off_t[j] = tap / (p.kh * p.kw) - p.pt;
+        off_h[j] = (tap / p.kw) % p.kh - p.ph;
+        off_w[j] = tap % p.kw - p.pw;
+      }
+      // box coordinates of the first k-step, then advanced incrementally with carries
       const int per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
+      int tn = ks_begin / per_sample;
+      int r = ks_begin - tn * per_sample;
+      int tw = r % p.tiles_w;
+      r /= p.tiles_w;
+      int th = r % p.tiles_h;
+      int tt = r / p.tiles_h;
+      const int panels = p.block_n / 64;
       for (int ks = ks_begin; ks < ks_end; ++ks) {
-        const int n = (ks / per_sample) << p.bn_log2;
-        int r = ks % per_sample;
-        const int w0 = (r % p.tiles_w) << p.bw_log2;
-        r /= p.tiles_w;
-        const int h0 = (r % p.tiles_h) << p.bh_log2;
-        const int t0 = (r / p.tiles_h) << p.bt_log2;
+        const int n = tn << p.bn_log2, w0 = tw << p.bw_log2, h0 = th << p.bh_log2, t0 = tt << p.bt_log2;
         mbar_wait(&empty_a[sa], pha ^ 1);
         mbar_expect_tx(&full_a[sa], kWABytes);
         tma_load_5d(smem_a + sa * kWABytes, &mapDY, &full_a[sa], co0, w0, h0, t0, n);
@@ -106,19 +129,35 @@ __global__ void __launch_bounds__(kWThreads, 1)
           sa = 0;
           pha ^= 1;
         }
-        for (int j = 0; j < ntap; ++j) {
-          const int tap = tap0 + j;
-          const int it = tap / (p.kh * p.kw);
-          const int ih = (tap / p.kw) % p.kh;
-          const int iw = tap % p.kw;
-          mbar_wait(&empty_b[sb], phb ^ 1);
-          mbar_expect_tx(&full_b[sb], (uint32_t)b_bytes);
-          for (int pp = 0; pp < p.block_n / 64; ++pp)
-            tma_load_5d(smem_b + sb * b_bytes + pp * kPanelBytes, &mapX, &full_b[sb], ci0 + pp * 64, w0 + iw - p.pw,
-                        h0 + ih - p.ph, t0 + it - p.pt, n);
-          if (++sb == p.b_stages) {
-            sb = 0;
-            phb ^= 1;
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          if (j < ntap) {
+            const int nt = (ntap - j) < 2 ? 1 : 2;
+            mbar_wait(&empty_b[sb], phb ^ 1);
+            mbar_expect_tx(&full_b[sb], (uint32_t)(nt * tap_bytes));
+            uint8_t* dst = smem_b + sb * b_bytes;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (u < nt) {
+                for (int pp = 0; pp < panels; ++pp)
+                  tma_load_5d(dst + u * tap_bytes + pp * kPanelBytes, &mapX, &full_b[sb], ci0 + pp * 64,
+                              w0 + off_w[j + u], h0 + off_h[j + u], t0 + off_t[j + u], n);
+              }
+            }
+            if (++sb == p.b_stages) {
+              sb = 0;
+              phb ^= 1;
+            }
+          }
+        }
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            if (++tt == p.tiles_t) {
+              tt = 0;
+              ++tn;
+            }
           }
         }
       }
@@ -126,18 +165,21 @@ __global__ void __launch_bounds__(kWThreads, 1)
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.block_n, 1u, 1u);
+      const uint32_t amn = (p.dbg & 1) ? 0u : 1u, bmn = (p.dbg & 2) ? 0u : 1u;
+      const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)p.block_n, amn, bmn);
+      const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * p.block_n), amn, bmn);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (int ks = ks_begin; ks < ks_end; ++ks) {
         mbar_wait(&full_a[sa], pha);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_a + sa * kWABytes);
-        for (int j = 0; j < ntap; ++j) {
+        for (int j = 0; j < ntap; j += 2) {
           mbar_wait(&full_b[sb], phb);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(smem_b + sb * b_bytes);
           const uint32_t d_tmem = tmem_base + j * p.block_n;
+          const uint32_t idesc = (ntap - j >= 2) ? idesc2 : idesc1;
 #pragma unroll
           for (int k = 0; k < kVox / 16; ++k) {
             // MN-major panels [panel][64 k-rows][128 B]: 16 k-rows = 2048 B, panel stride = 8192 B
@@ -163,9 +205,12 @@ __global__ void __launch_bounds__(kWThreads, 1)
   } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
+    if (p.dbg & 8)
+      mbar_wait(tmem_full, 0);
+    else
+      mbar_wait_relaxed(tmem_full, 0);
     tc_fence_after();
-    for (int j = 0; j < ntap; ++j) {
+    for (int j = 0; j < ntap && !(p.dbg & 4); ++j) {
       const int tap = tap0 + j;
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t v[32];
@@ -173,9 +218,18 @@ __global__ void __launch_bounds__(kWThreads, 1)
         tmem_ld_wait();
         if (co < p.cout) {
           float* dst = p.dw + (long long)co * p.ld_dw + (long long)tap * p.cin + ci0 + c;
+          if (p.vec_ok && ci0 + c + 32 <= p.cin) {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj)
-            if (ci0 + c + jj < p.cin) atomicAdd(dst + jj, __uint_as_float(v[jj]));
+            for (int jj = 0; jj < 32; jj += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + jj), "f"(__uint_as_float(v[jj])),
+                           "f"(__uint_as_float(v[jj + 1])), "f"(__uint_as_float(v[jj + 2])),
+                           "f"(__uint_as_float(v[jj + 3]))
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (ci0 + c + jj < p.cin) atomicAdd(dst + jj, __uint_as_float(v[jj]));
+          }
         }
       }
     }
@@ -219,15 +273,32 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
   const int co_tiles = (cout + 127) / 128;
   const int ci_tiles = cin / p.block_n;
   const int base_ctas = co_tiles * ci_tiles * p.num_groups;
-  int splitk = (2 * num_sms() + base_ctas - 1) / base_ctas;  // ~2 CTAs' worth of work items per SM
-  if (splitk < 1) splitk = 1;
-  // keep at least 8 k-steps per CTA so the pipeline fill / epilogue atomics are amortised
-  int max_split = p.num_ksteps / 8;
+  // split-K factor: fill whole waves (a partial last wave costs a full CTA duration), keep >= 4 k-steps per
+  // CTA so pipeline fill and the epilogue reductions stay amortised, at most ~3 waves.
+  const int sms = num_sms();
+  int max_split = p.num_ksteps / 4;
   if (max_split < 1) max_split = 1;
-  if (splitk > max_split) splitk = max_split;
-  if (splitk > p.num_ksteps) splitk = p.num_ksteps;
+  if (max_split > 128) max_split = 128;
+  int splitk = 1;
+  double best = -1.0;
+  for (int s = 1; s <= max_split; ++s) {
+    const long long total = (long long)base_ctas * s;
+    const long long waves = (total + sms - 1) / sms;
+    if (waves > 3 && s > 1) break;
+    const double eff = (double)total / (double)(waves * sms);
+    // prefer higher wave efficiency; among equals prefer fewer splits (fewer reductions)
+    if (eff > best + 1e-9) {
+      best = eff;
+      splitk = s;
+    }
+  }
   p.splitk = splitk;
-  const int b_bytes = (p.block_n / 64) * kPanelBytes;
+  {
+    const char* e = getenv("OG_WGRAD_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  p.vec_ok = (ld_dw % 4 == 0) && (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
+  const int b_bytes = 2 * (p.block_n / 64) * kPanelBytes;  // a pair of taps per stage
   p.a_stages = 3;
   p.b_stages = (int)((216 * 1024 - p.a_stages * kWABytes) / b_bytes);
   if (p.b_stages > kWMaxStages) p.b_stages = kWMaxStages;
@@ -255,7 +326,7 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid(co_tiles, ci_tiles, p.num_groups * p.splitk);
+  dim3 grid(co_tiles, ci_tiles, p.num_groups * p.splitk);  // z = split * num_groups + group
   og_conv_wgrad_kernel<<<grid, kWThreads, smem_bytes, (cudaStream_t)stream>>>(mapDY, mapX, p);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);

@@ -59,6 +59,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait used by warps that have nothing to do for a long time (epilogue warps during a main loop):
+// back off with nanosleep so the pollers do not steal issue slots / smem cycles from the TMA and MMA warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(spins < 64 ? 64 : 512);
+    if (++spins > (OG_MBAR_SPIN_LIMIT >> 2)) {
+      printf("og: mbarrier (relaxed) wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA loads (tile mode). Destination is this CTA's shared memory, completion on an mbarrier.
 // ----------------------------------------------------------------------------------------------

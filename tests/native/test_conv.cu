@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -362,11 +363,17 @@ int main(int argc, char** argv) {
       {1, 4, 32, 32, 256, 0, 1024, 3, 3, 3, 2, 1, 1, true},  // up-conv shape (N heavy)
   };
   bool all_ok = true;
-  for (size_t i = 0; i < cases.size(); ++i) {
+  const bool bench_only = argc > 1 && !strcmp(argv[1], "benchonly");
+  for (size_t i = 0; i < cases.size() && !bench_only; ++i) {
     if (quick && i > 3) break;
     all_ok &= run_case(cases[i], true, true);
   }
   printf("RESULT: %s\n", all_ok ? "ALL PASS" : "FAILURES");
+  if (bench_only) {
+    const int it = argc > 2 ? atoi(argv[2]) : 1;
+    bench_case({8, 16, 64, 64, 128, 0, 128, 3, 3, 3, 1, 1, 1, false}, it);
+    bench_case({8, 4, 8, 8, 512, 0, 512, 3, 3, 3, 1, 1, 1, false}, it);
+  }
   if (argc > 1 && !strcmp(argv[1], "bench")) {
     bench_case({8, 16, 64, 64, 128, 0, 128, 3, 3, 3, 1, 1, 1, false}, 5);
     bench_case({8, 16, 32, 32, 256, 0, 256, 3, 3, 3, 1, 1, 1, false}, 5);
