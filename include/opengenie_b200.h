@@ -201,9 +201,13 @@ int og_adamw_chunk_elems(void);
 /* table_dev: device array of tensors; chunk_tensor_dev / chunk_index_dev: for every chunk of
  * og_adamw_chunk_elems() elements, which tensor and which chunk inside it. step >= 1.
  * grad_scale_dev: optional device scalar multiplied into every gradient (e.g. 1/world_size). */
+/* step_dev / lr_dev (optional): step count and learning rate read from device memory instead of the
+ * host arguments, so a CUDA graph that captured the whole training step stays valid across replays;
+ * og_adamw_tick increments the device-side step counter (launch it before og_adamw_step). */
 int og_adamw_step(const og_adamw_tensor* table_dev, const int* chunk_tensor_dev, const int* chunk_index_dev,
                   int num_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                  const float* grad_scale_dev, og_stream_t stream);
+                  const int* step_dev, const float* lr_dev, const float* grad_scale_dev, og_stream_t stream);
+int og_adamw_tick(int* step_dev, og_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,7 @@ struct IgemmParams {
   int num_stages;
   int num_kb;  // k-blocks per tile
   int m_sub;   // M sub-tiles (of 128 rows) per CTA tile sharing one B stage: 1 or 2
+  int fast_store;  // bf16 output, n_out % 64 == 0, block_n % 64 == 0: coalesced staged stores
 };
 
 static constexpr int kBlockM = 128;
@@ -96,6 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* bias_s = reinterpret_cast<float*>(bars + 32);                    // [256] bias0+bias1 of the current N tile
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>(bars + 32) + 1024;        // 4 warps x 32 rows x 128 B store staging
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,6 +241,63 @@ __global__ void __launch_bounds__(kThreads, 1)
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ms * p.block_n + ((uint32_t)(q * 32) << 16);
 
+      if (p.fast_store) {
+        // bf16 output, whole 64-column chunks: registers -> (bias) -> bf16 -> swizzled smem staging -> the warp
+        // writes 4 full 128-byte row segments per instruction (the row-per-thread TMEM layout would otherwise
+        // scatter 16-byte pieces over 32 different lines per store).
+        if (ms == 0) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's bias readers are done
+          for (int j = threadIdx.x - 64; j < p.block_n; j += 128) {
+            const int col = col0 + j;
+            float b = 0.f;
+            if (col < p.n_out) {
+              if (p.bias0) b += __ldg(p.bias0 + col);
+              if (p.bias1) b += __ldg(p.bias1 + col);
+            }
+            bias_s[j] = b;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        uint8_t* my_stage = stage_s + (warp - 2) * 4096;
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+        for (int c = 0; c < p.block_n; c += 64) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(t_addr + c, v0);
+          tmem_ld_32x32(t_addr + c + 32, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]) + bias_s[c + 8 * j + 0], __uint_as_float(v0[8 * j + 1]) + bias_s[c + 8 * j + 1]);
+            u.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]) + bias_s[c + 8 * j + 2], __uint_as_float(v0[8 * j + 3]) + bias_s[c + 8 * j + 3]);
+            u.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]) + bias_s[c + 8 * j + 4], __uint_as_float(v0[8 * j + 5]) + bias_s[c + 8 * j + 5]);
+            u.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]) + bias_s[c + 8 * j + 6], __uint_as_float(v0[8 * j + 7]) + bias_s[c + 8 * j + 7]);
+            *reinterpret_cast<uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]) + bias_s[c + 32 + 8 * j + 0], __uint_as_float(v1[8 * j + 1]) + bias_s[c + 32 + 8 * j + 1]);
+            u.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]) + bias_s[c + 32 + 8 * j + 2], __uint_as_float(v1[8 * j + 3]) + bias_s[c + 32 + 8 * j + 3]);
+            u.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]) + bias_s[c + 32 + 8 * j + 4], __uint_as_float(v1[8 * j + 5]) + bias_s[c + 32 + 8 * j + 5]);
+            u.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]) + bias_s[c + 32 + 8 * j + 6], __uint_as_float(v1[8 * j + 7]) + bias_s[c + 32 + 8 * j + 7]);
+            *reinterpret_cast<uint4*>(my_stage + lane * 128 + (((j + 4) ^ (lane & 7)) << 4)) = u;
+          }
+          __syncwarp();
+          const int chunk = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            const long long rvox = __shfl_sync(0xffffffffu, vox, r);
+            const int rok = __shfl_sync(0xffffffffu, (int)row_ok, r);
+            const uint4 u = *reinterpret_cast<const uint4*>(my_stage + r * 128 + ((chunk ^ (r & 7)) << 4));
+            if (rok) *reinterpret_cast<uint4*>(outp + rvox * p.ldo + col0 + c + chunk * 8) = u;
+          }
+          __syncwarp();
+        }
+        continue;
+      }
+
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t v[32];
         if (p.block_n >= 32) {
@@ -370,10 +430,12 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   // 128-row M sub-tiles keeps the demand at (32+16) KB per 512 MMA-clk (same as a 128x256 tile).
   p.m_sub = (p.block_n <= 128 && p.num_m_tiles >= 2 * num_sms()) ? 2 : 1;
   const int stage_bytes = p.m_sub * kABytes + p.block_n * kBlockK * 2;
-  int stages = (220 * 1024) / stage_bytes;
+  p.fast_store = (!out_f32 && n_out % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
+  const int tail_bytes = 256 /*barriers*/ + 1024 /*bias*/ + 4 * 4096 /*store staging*/;
+  int stages = (227 * 1024 - 1024 /*align slack*/ - tail_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + tail_bytes;
 
   CUtensorMap mapA0, mapA1, mapB;
   {

@@ -15,8 +15,18 @@ static constexpr int kChunk = 2048;  // elements per block-iteration
 __global__ void __launch_bounds__(256)
     og_adamw_kernel(const og_adamw_tensor* __restrict__ table, const int* __restrict__ chunk_tensor,
                     const int* __restrict__ chunk_index, int num_chunks, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, float bc1, float bc2, const float* __restrict__ grad_scale) {
+                    float eps, float weight_decay, float bc1_host, float bc2_host, const int* __restrict__ step_dev,
+                    const float* __restrict__ lr_dev, const float* __restrict__ grad_scale) {
   const float gs = grad_scale ? *grad_scale : 1.f;
+  // step count / learning rate may live in device memory so that a captured CUDA graph of the whole
+  // training step stays valid across replays (host scalars would be frozen at capture time)
+  float bc1 = bc1_host, bc2 = bc2_host;
+  if (step_dev) {
+    const float t = (float)(*step_dev);
+    bc1 = 1.f - powf(beta1, t);
+    bc2 = sqrtf(1.f - powf(beta2, t));
+  }
+  if (lr_dev) lr = *lr_dev;
   for (int ch = blockIdx.x; ch < num_chunks; ch += gridDim.x) {
     const og_adamw_tensor t = table[chunk_tensor[ch]];
     const long long base = (long long)chunk_index[ch] * kChunk;
@@ -50,17 +60,28 @@ using namespace og;
 
 extern "C" int og_adamw_chunk_elems(void) { return kChunk; }
 
+__global__ void og_adamw_tick_kernel(int* step) { *step += 1; }
+
+extern "C" int og_adamw_tick(int* step_dev, og_stream_t stream) {
+  OG_REQUIRE(step_dev, "adamw_tick: null pointer");
+  og_adamw_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
 extern "C" int og_adamw_step(const og_adamw_tensor* table_dev, const int* chunk_tensor_dev, const int* chunk_index_dev,
                              int num_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
-                             int step, const float* grad_scale_dev, og_stream_t stream) {
+                             int step, const int* step_dev, const float* lr_dev, const float* grad_scale_dev,
+                             og_stream_t stream) {
   OG_REQUIRE(table_dev && chunk_tensor_dev && chunk_index_dev && num_chunks > 0 && step >= 1,
              "adamw_step: bad arguments");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2 = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   int grid = num_sms() * 8;
   if (grid > num_chunks) grid = num_chunks;
   og_adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, chunk_tensor_dev, chunk_index_dev, num_chunks, lr,
-                                                         beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale_dev);
+                                                         beta1, beta2, eps, weight_decay, bc1, bc2, step_dev, lr_dev, grad_scale_dev);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;

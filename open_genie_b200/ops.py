@@ -36,7 +36,7 @@ def _conv_call(kind: str, flops: float, name: str, *args):
     e0.record()
     _lib.call(name, *args)
     e1.record()
-    PROFILE.append((kind, flops, e0, e1))
+    PROFILE.append((kind, flops, e0, e1, tuple(a for a in args if isinstance(a, int) and a < (1 << 20))))
 
 
 def _ptr(t: Optional[Tensor]):

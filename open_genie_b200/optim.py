@@ -22,6 +22,8 @@ class FusedAdamW(Optimizer):
         self._dev_table = self._dev_ct = self._dev_ci = None
         self._num_chunks = 0
         self.grad_scale: Optional[torch.Tensor] = None   # device scalar multiplied into every gradient
+        self._step_dev: Optional[torch.Tensor] = None    # device-side step counter (CUDA-graph safe)
+        self._pinned = []                                # host staging buffers referenced by captured copies
 
     def _bf16_target(self, p):
         """Packed bf16 operand (tensor, column offset) of the conv that owns parameter p, if any."""
@@ -63,6 +65,9 @@ class FusedAdamW(Optimizer):
         if not entries:
             return loss
         self._step += 1
+        if self._step_dev is None:
+            self._step_dev = torch.full((1,), self._step - 1, dtype=torch.int32, device=entries[0][0].device)
+        _lib.call('og_adamw_tick', self._step_dev.data_ptr(), torch.cuda.current_stream().cuda_stream)
         # one launch per param group (hyper-parameters are launch arguments)
         by_group = {}
         for e in entries:
@@ -103,11 +108,14 @@ class FusedAdamW(Optimizer):
                 else:
                     t.p_bf16, t.row_len, t.dst_ld = None, 1, 1
             raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).pin_memory()
+            self._pinned.append(raw)        # keep alive: a captured graph replays this H2D copy
+            if len(self._pinned) > 8 and not torch.cuda.is_current_stream_capturing():
+                del self._pinned[:-8]
             self._dev_table = raw.to(dev, non_blocking=True)
             self._cache_key = key
         b1, b2 = group['betas']
+        stream = torch.cuda.current_stream().cuda_stream
         _lib.call('og_adamw_step', self._dev_table.data_ptr(), self._dev_ct.data_ptr(), self._dev_ci.data_ptr(),
                   self._num_chunks, float(group['lr']), float(b1), float(b2), float(group['eps']),
-                  float(group['weight_decay']), self._step,
-                  None if self.grad_scale is None else self.grad_scale.data_ptr(),
-                  torch.cuda.current_stream().cuda_stream)
+                  float(group['weight_decay']), self._step, self._step_dev.data_ptr(), None,
+                  None if self.grad_scale is None else self.grad_scale.data_ptr(), stream)
