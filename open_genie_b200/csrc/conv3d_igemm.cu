@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         uint8_t* my_stage = stage_s + (warp - 2) * 4096;
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
         for (int c = 0; c < p.block_n; c += 64) {
+          if (col0 + c >= p.n_out) break;  // partial last N tile (n_out % 64 == 0, so chunks are all-or-nothing)
           uint32_t v0[32], v1[32];
           tmem_ld_32x32(t_addr + c, v0);
           tmem_ld_32x32(t_addr + c + 32, v1);

@@ -195,19 +195,22 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
   // bf16 output path
   {
     __nv_bfloat16* ob;
-    CK(cudaMalloc(&ob, V * c.cout * 2));
+    CK(cudaMalloc(&ob, (V * c.cout + 64) * 2));
+    CK(cudaMemset(ob, 0x7F, (V * c.cout + 64) * 2));
     r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, x1, c.c1, w, ldw, b0, b1, ob, 0, c.N, c.T, c.H,
                       c.W, c.cout, 0);
     CK(cudaDeviceSynchronize());
-    std::vector<__nv_bfloat16> hb(V * c.cout);
+    std::vector<__nv_bfloat16> hb(V * c.cout + 64);
     std::vector<float> hr(V * c.cout);
-    CK(cudaMemcpy(hb.data(), ob, V * c.cout * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hb.data(), ob, hb.size() * 2, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hr.data(), ref, V * c.cout * 4, cudaMemcpyDeviceToHost));
     size_t bad = 0;
-    for (size_t i = 0; i < hb.size(); ++i) {
+    for (size_t i = 0; i < hr.size(); ++i) {
       float g = __bfloat162float(hb[i]);
       if (!(fabsf(g - hr[i]) <= 2e-3f + 8e-3f * fabsf(hr[i]))) ++bad;
     }
+    for (size_t i = hr.size(); i < hb.size(); ++i)
+      if (*reinterpret_cast<uint16_t*>(&hb[i]) != 0x7F7F) ++bad;  // wrote past the end
     printf("  %-28s mismatches=%zu %s\n", "fwd(bf16 out)", bad, bad ? "FAIL" : "ok");
     ok &= bad == 0;
     CK(cudaFree(ob));
@@ -235,6 +238,25 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
                                                          dxr, c.N, c.T, c.H, c.W, c.c0);
       CK(cudaDeviceSynchronize());
       ok &= compare("dgrad(main segment)", dx, dxr, V * c.c0, 1e-3f, 1e-3f);
+      // bf16 output (the product path): exercises the coalesced staged store, incl. partial last N tiles
+      __nv_bfloat16* dxb;
+      CK(cudaMalloc(&dxb, (V * c.c0 + 64) * 2));
+      CK(cudaMemset(dxb, 0x7F, (V * c.c0 + 64) * 2));  // canary after the tensor
+      r = og_conv3d_dgrad(dy, c.cout, c.cout, w, ldw, 0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, dxb, 0, c.N, c.T, c.H, c.W,
+                          c.c0, 0);
+      CK(cudaDeviceSynchronize());
+      std::vector<__nv_bfloat16> hb(V * c.c0 + 64);
+      std::vector<float> hr(V * c.c0);
+      CK(cudaMemcpy(hb.data(), dxb, hb.size() * 2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hr.data(), dxr, hr.size() * 4, cudaMemcpyDeviceToHost));
+      size_t bad = 0;
+      for (size_t i = 0; i < hr.size(); ++i)
+        if (!(fabsf(__bfloat162float(hb[i]) - hr[i]) <= 2e-3f + 8e-3f * fabsf(hr[i]))) ++bad;
+      for (size_t i = hr.size(); i < hb.size(); ++i)
+        if (*reinterpret_cast<uint16_t*>(&hb[i]) != 0x7F7F) ++bad;  // wrote past the end
+      printf("  %-28s mismatches=%zu %s\n", "dgrad(bf16 out + canary)", bad, bad ? "FAIL" : "ok");
+      ok &= bad == 0;
+      CK(cudaFree(dxb));
     }
     if (c.c1 && c.c1 % 64 == 0) {
       float *dx1, *dx1r;
@@ -361,6 +383,12 @@ int main(int argc, char** argv) {
       {2, 2, 16, 16, 64, 0, 18, 1, 1, 1, 0, 0, 0, true},     // Cout=18 (encoder head): masked scalar epilogue
       {1, 2, 64, 64, 128, 0, 3, 3, 3, 3, 2, 1, 1, true},     // Cout=3 (decoder tail), W=64 box
       {1, 4, 32, 32, 256, 0, 1024, 3, 3, 3, 2, 1, 1, true},  // up-conv shape (N heavy)
+      {2, 8, 32, 32, 64, 0, 64, 1, 1, 1, 0, 0, 0, true},     // 1x1x1, many short tiles (2 k-blocks): epilogue-bound
+      {1, 1, 1, 16384, 128, 0, 64, 1, 1, 1, 0, 0, 0, true},  // flattened im2col GEMM view (1,1,1,M)
+      {1, 1, 1, 4100, 128, 0, 64, 1, 1, 1, 0, 0, 0, false},  // M not a multiple of the tile: partial boxes
+      {3, 4, 8, 8, 64, 0, 128, 3, 3, 3, 1, 1, 1, true},      // odd batch with 2-row-block tiles
+      {1, 2, 16, 16, 64, 0, 320, 1, 1, 1, 0, 0, 0, true},    // Cout = 320: partial last 256-wide N tile, bf16 fast store
+      {8, 16, 64, 64, 64, 64, 64, 3, 3, 3, 1, 1, 1, true},   // enough tiles for the 256-row (m_sub = 2) path
   };
   bool all_ok = true;
   const bool bench_only = argc > 1 && !strcmp(argv[1], "benchonly");
