@@ -59,10 +59,12 @@ uint64_t og_launch_count(void);
  * x0: bf16 [N,T,H,W,c0], c0 % 64 == 0.  x1: bf16 [N,T,H,W,c1] or NULL (c1 % 64 == 0).
  * w : bf16 [cout][ldw], ldw >= kt*kh*kw*c0 + c1, ldw % 8 == 0.
  * out: [N,T,H,W,cout], bf16 or fp32 (out_f32 != 0). bias0/bias1: fp32 [cout] or NULL.
- * Reads outside [0,T)x[0,H)x[0,W) are zero (pad_mode='constant'). */
+ * Reads outside [0,T)x[0,H)x[0,W) are zero (pad_mode='constant').
+ * workspace (optional, may be NULL): N*T*H*W*cout fp32 of scratch enables split-K for problems whose tiles
+ * cannot fill the 148 SMs (small T*H*W, deep K); without it the same result is computed unsplit. */
 int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1, int c1,
                   const void* w, int ldw, const float* bias0, const float* bias1, void* out, int out_f32, int N,
-                  int T, int H, int W, int cout, og_stream_t stream);
+                  int T, int H, int W, int cout, void* workspace, size_t workspace_bytes, og_stream_t stream);
 
 /* Data gradient of the same convolution (autograd's conv3d backward-input, reached from
  * video.py:192 / 609-629 / 599-603 during loss.backward()).
@@ -72,7 +74,7 @@ int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph
  * a packed row, k_off % 8 == 0); dx: [N,T,H,W,cin] (cin % 64 == 0), bf16 or fp32. */
 int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int k_off, int kt, int kh, int kw,
                     int pt, int ph, int pw, void* dx, int dx_f32, int N, int T, int H, int W, int cin,
-                    og_stream_t stream);
+                    void* workspace, size_t workspace_bytes, og_stream_t stream);
 
 /* Weight gradient (autograd's conv3d backward-weight). ACCUMULATES into dw (caller zeroes it):
  *   dw[co][tap][ci] += sum_{n,t,h,w} dy[n,t,h,w,co] * x[n, t+it-pt, h+ih-ph, w+iw-pw, ci]

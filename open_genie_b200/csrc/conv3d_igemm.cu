@@ -19,6 +19,8 @@
 //   warp 0    TMA producer (one elected lane)
 //   warp 1    TMEM allocator + MMA issuer (one elected lane)
 //   warps 2-5 epilogue: TMEM -> registers -> (+bias) -> global, double-buffered against the next tile's MMAs
+#include <stdlib.h>
+
 #include "og_host.cuh"
 #include "og_ptx.cuh"
 
@@ -52,6 +54,8 @@ struct IgemmParams {
   int num_kb;  // k-blocks per tile
   int m_sub;   // M sub-tiles (of 128 rows) per CTA tile sharing one B stage: 1 or 2
   int fast_store;  // bf16 output, n_out % 64 == 0, block_n % 64 == 0: coalesced staged stores
+  int splits;      // split-K factor (1 = none): each work item covers a k-block range and reduces into `ws`
+  float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zeroed by the launcher) when splits > 1
 };
 
 static constexpr int kBlockM = 128;
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_m_super = (p.num_m_tiles + p.m_sub - 1) / p.m_sub;
-  const int total_tiles = num_m_super * p.num_n_tiles;
+  const int total_tiles = num_m_super * p.num_n_tiles * p.splits;  // work items
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -130,45 +134,62 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / p.splits, split = item - tile * p.splits;
         const int m_super = tile / p.num_n_tiles;
         const int n_tile = tile - m_super * p.num_n_tiles;
         const TileCoord tc = decode_m_tile(p, m_super * p.m_sub);
         const TileCoord tc1 = decode_m_tile(p, m_super * p.m_sub + 1);  // second sub-tile (m_sub == 2)
-        int kb = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const IgemmSeg sg = p.seg[s];
-          const CUtensorMap* mapA = (s == 0) ? &mapA0 : &mapA1;
-          int tap = 0;
-          for (int it = 0; it < sg.kt; ++it)
-            for (int ih = 0; ih < sg.kh; ++ih)
-              for (int iw = 0; iw < sg.kw; ++iw, ++tap) {
-                const int ct = tc.t0 + p.sgn * (it - sg.pt);
-                const int ch = tc.h0 + p.sgn * (ih - sg.ph);
-                const int cw = tc.w0 + p.sgn * (iw - sg.pw);
-                for (int cb = 0; cb < sg.cin_blocks; ++cb, ++kb) {
-                  mbar_wait(&empty[stage], phase ^ 1);
-                  uint8_t* sa = smem + stage * stage_bytes;
-                  uint8_t* sb = sa + a_bytes;
-                  mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                  tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, cw, ch, ct, tc.n0);
-                  if (p.m_sub == 2)
-                    tma_load_5d(sa + kABytes, mapA, &full[stage], cb * kBlockK, tc1.w0 + p.sgn * (iw - sg.pw),
-                                tc1.h0 + p.sgn * (ih - sg.ph), tc1.t0 + p.sgn * (it - sg.pt), tc1.n0);
-                  if (!p.b_mn_major) {
-                    tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
-                  } else {
-                    // w[co][tap][ci] as (ci, tap, co): one (64 ci, 1 tap, 64 co) box per 64-wide N panel
-                    for (int pp = 0; pp < p.block_n / 64; ++pp)
-                      tma_load_3d(sb + pp * (64 * 128), &mapB, &full[stage], n_tile * p.block_n + pp * 64, tap,
-                                  cb * kBlockK);
-                  }
-                  if (++stage == p.num_stages) {
-                    stage = 0;
-                    phase ^= 1;
-                  }
+        const int kb_begin = (int)(((long long)p.num_kb * split) / p.splits);
+        const int kb_end = (int)(((long long)p.num_kb * (split + 1)) / p.splits);
+        // position (segment, tap = (it, ih, iw), channel block) of kb_begin: divisions once per work item,
+        // then the single producer thread only increments with carries (its instruction count per k-block
+        // is what bounds the pipeline when MMAs are short)
+        const int nkb0 = p.seg[0].cin_blocks * p.seg[0].kt * p.seg[0].kh * p.seg[0].kw;
+        int sidx = (kb_begin >= nkb0 && p.nseg > 1) ? 1 : 0;
+        IgemmSeg sg = p.seg[sidx];
+        int rel = kb_begin - (sidx ? nkb0 : 0);
+        int tap = rel / sg.cin_blocks;
+        int cb = rel - tap * sg.cin_blocks;
+        int it = tap / (sg.kh * sg.kw);
+        int ih = (tap / sg.kw) % sg.kh;
+        int iw = tap % sg.kw;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const CUtensorMap* mapA = (sidx == 0) ? &mapA0 : &mapA1;
+          const int dt = p.sgn * (it - sg.pt), dh = p.sgn * (ih - sg.ph), dw = p.sgn * (iw - sg.pw);
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+          tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n0);
+          if (p.m_sub == 2)
+            tma_load_5d(sa + kABytes, mapA, &full[stage], cb * kBlockK, tc1.w0 + dw, tc1.h0 + dh, tc1.t0 + dt, tc1.n0);
+          if (!p.b_mn_major) {
+            tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
+          } else {
+            // w[co][tap][ci] as (ci, tap, co): one (64 ci, 1 tap, 64 co) box per 64-wide N panel
+            for (int pp = 0; pp < p.block_n / 64; ++pp)
+              tma_load_3d(sb + pp * (64 * 128), &mapB, &full[stage], n_tile * p.block_n + pp * 64, tap, cb * kBlockK);
+          }
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++cb == sg.cin_blocks) {
+            cb = 0;
+            ++tap;
+            if (++iw == sg.kw) {
+              iw = 0;
+              if (++ih == sg.kh) {
+                ih = 0;
+                if (++it == sg.kt) {  // next segment (the fused 1x1x1 shortcut)
+                  sidx = 1;
+                  sg = p.seg[1];
+                  it = ih = iw = tap = 0;
                 }
               }
+            }
+          }
         }
       }
     }
@@ -181,11 +202,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int nkb = (int)(((long long)p.num_kb * (split + 1)) / p.splits) -
+                        (int)(((long long)p.num_kb * split) / p.splits);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
@@ -223,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+      const int tile = item / p.splits;
       const int m_super = tile / p.num_n_tiles;
       const int n_tile = tile - m_super * p.num_n_tiles;
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
@@ -240,6 +265,31 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int col0 = n_tile * p.block_n;
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ms * p.block_n + ((uint32_t)(q * 32) << 16);
+
+      if (p.splits > 1) {
+        // split-K: add this item's partial sums into the fp32 workspace (bias / cast happen in the finish pass)
+        for (int c = 0; c < p.block_n; c += 32) {
+          if (col0 + c >= p.n_out) break;
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + c, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* dst = p.ws + vox * p.ldo + col0 + c;
+            if (p.vec_ok && col0 + c + 32 <= p.n_out) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                             "f"(__uint_as_float(v[j + 3]))
+                             : "memory");
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (col0 + c + j < p.n_out) atomicAdd(dst + j, __uint_as_float(v[j]));
+            }
+          }
+        }
+        continue;
+      }
 
       if (p.fast_store) {
         // bf16 output, whole 64-column chunks: registers -> (bias) -> bf16 -> swizzled smem staging -> the warp
@@ -370,29 +420,41 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+// split-K finish: out = cast(ws + bias0 + bias1)
+__global__ void og_splitk_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias0,
+                                        const float* __restrict__ bias1, void* __restrict__ out, int out_f32,
+                                        int n_out, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % n_out);
+    float v = ws[i];
+    if (bias0) v += __ldg(bias0 + col);
+    if (bias1) v += __ldg(bias1 + col);
+    if (out_f32)
+      reinterpret_cast<float*>(out)[i] = v;
+    else
+      reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static int pick_block_n(int n_out, int num_m_tiles, bool mn_major) {
-  // largest N tile that still yields >= one wave of tiles; never below 64 for MN-major B (64-wide panels)
-  const int sms = num_sms();
-  int cap = 16;
-  while (cap < n_out && cap < 256) cap *= 2;
-  const int floor_n = mn_major ? 64 : 16;
-  if (cap < floor_n) cap = floor_n;
-  int bn = cap;
-  while (bn > floor_n && bn > 64) {
-    long long tiles = (long long)num_m_tiles * ((n_out + bn - 1) / bn);
-    if (tiles >= sms) break;
-    bn /= 2;
-  }
+  // The widest N tile that covers n_out (<= 256). Measured on B200: fewer, fatter tiles beat more, thinner ones
+  // even when they leave SMs idle (a 128x256 tile streams 96 B/MMA-clk, a 128x64 one 192 B/MMA-clk, and the
+  // TMA-latency x smem-capacity product caps what one SM can stream); low tile counts are handled by split-K.
+  int bn = 16;
+  while (bn < n_out && bn < 256) bn *= 2;
+  if (mn_major && bn < 64) bn = 64;
+  (void)num_m_tiles;
   return bn;
 }
 
 static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const IgemmSeg* segs, int nseg, int sgn,
                         const void* w, int ldw, int k_off, int b_mn_major, int b_rows /*K rows for MN-major*/,
                         int b_ntaps, const float* bias0, const float* bias1, void* out, int out_f32, int N, int T,
-                        int H, int W, int n_out, cudaStream_t stream) {
+                        int H, int W, int n_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   OG_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0 && n_out > 0, "conv3d: empty problem");
   int bw, bh, bt, bn;
   choose_voxel_box(kBlockM, N, T, H, W, &bw, &bh, &bt, &bn);
@@ -419,6 +481,10 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   p.W = W;
   p.num_m_tiles = ((N + bn - 1) / bn) * p.tiles_w * p.tiles_h * p.tiles_t;
   p.block_n = pick_block_n(n_out, p.num_m_tiles, b_mn_major != 0);
+  if (const char* e = getenv("OG_IGEMM_BN")) {  // tuning experiments only
+    const int v = atoi(e);
+    if (v >= 16 && v <= 256 && (!b_mn_major || v >= 64)) p.block_n = v;
+  }
   p.num_n_tiles = (n_out + p.block_n - 1) / p.block_n;
   p.n_out = n_out;
   p.ldo = n_out;
@@ -430,8 +496,29 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   // TMA latency x smem capacity bounds the bytes/clk one SM can stream; sharing each B stage between two
   // 128-row M sub-tiles keeps the demand at (32+16) KB per 512 MMA-clk (same as a 128x256 tile).
   p.m_sub = (p.block_n <= 128 && p.num_m_tiles >= 2 * num_sms()) ? 2 : 1;
+  if (const char* e = getenv("OG_IGEMM_MSUB")) {
+    const int v = atoi(e);
+    if ((v == 1 || v == 2) && v * p.block_n <= 256) p.m_sub = v;
+  }
   const int stage_bytes = p.m_sub * kABytes + p.block_n * kBlockK * 2;
   p.fast_store = (!out_f32 && n_out % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
+  // split-K when the tiles cannot fill the machine and each has a long K loop
+  p.splits = 1;
+  p.ws = nullptr;
+  {
+    const long long tiles = (long long)((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles;
+    const size_t need = (size_t)N * T * H * W * n_out * sizeof(float);
+    if (tiles * 2 <= num_sms() && p.num_kb >= 32 && workspace && workspace_bytes >= need) {
+      int sp = (int)(num_sms() / tiles);
+      if (sp > p.num_kb / 8) sp = p.num_kb / 8;
+      if (sp > 16) sp = 16;
+      if (sp >= 2) {
+        p.splits = sp;
+        p.ws = reinterpret_cast<float*>(workspace);
+        OG_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, stream));
+      }
+    }
+  }
   const int tail_bytes = 256 /*barriers*/ + 1024 /*bias*/ + 4 * 4096 /*store staging*/;
   int stages = (227 * 1024 - 1024 /*align slack*/ - tail_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -478,12 +565,20 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int total_tiles = ((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles;
+  const int total_tiles = ((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles * p.splits;
   int grid = num_sms();
   if (grid > total_tiles) grid = total_tiles;
   og_conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapB, p);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
+  if (p.splits > 1) {
+    const long long total = (long long)N * T * H * W * n_out;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    og_splitk_finish_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p.ws, bias0, bias1, out, out_f32, n_out, total);
+    OG_CHECK_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+  }
   return OG_OK;
 }
 
@@ -491,7 +586,8 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
 
 extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1,
                              int c1, const void* w, int ldw, const float* bias0, const float* bias1, void* out,
-                             int out_f32, int N, int T, int H, int W, int cout, og_stream_t stream) {
+                             int out_f32, int N, int T, int H, int W, int cout, void* workspace, size_t workspace_bytes,
+                             og_stream_t stream) {
   using namespace og;
   OG_REQUIRE(x0 && w && out, "conv3d_fwd: null pointer");
   OG_REQUIRE(c0 > 0 && c0 % 64 == 0, "conv3d_fwd: c0=%d must be a positive multiple of 64 (use the im2col path)", c0);
@@ -504,12 +600,12 @@ extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int
   segs[0] = IgemmSeg{c0 / 64, kt, kh, kw, pt, ph, pw};
   segs[1] = IgemmSeg{c1 / 64, 1, 1, 1, 0, 0, 0};
   return launch_igemm(x0, c0, x1, c1, segs, x1 ? 2 : 1, +1, w, ldw, 0, 0, 0, 0, bias0, bias1, out, out_f32, N, T, H, W,
-                      cout, (cudaStream_t)stream);
+                      cout, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int k_off, int kt, int kh,
                                int kw, int pt, int ph, int pw, void* dx, int dx_f32, int N, int T, int H, int W,
-                               int cin, og_stream_t stream) {
+                               int cin, void* workspace, size_t workspace_bytes, og_stream_t stream) {
   using namespace og;
   OG_REQUIRE(dy && w && dx, "conv3d_dgrad: null pointer");
   OG_REQUIRE(cout > 0 && cout % 64 == 0, "conv3d_dgrad: cout=%d must be a multiple of 64", cout);
@@ -519,5 +615,5 @@ extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void*
   IgemmSeg segs[1];
   segs[0] = IgemmSeg{cout / 64, kt, kh, kw, pt, ph, pw};
   return launch_igemm(dy, cout, nullptr, 0, segs, 1, -1, w, ldw, k_off, 1, w_rows, kt * kh * kw, nullptr, nullptr, dx,
-                      dx_f32, N, T, H, W, cin, (cudaStream_t)stream);
+                      dx_f32, N, T, H, W, cin, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -244,26 +244,29 @@ __global__ void og_colsum_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
-// vectorised column sums for ld % 8 == 0: thread -> (8-channel vector, row lane); 4 independent 16-byte loads
-// in flight per thread; fp32 partials -> shared atomics -> one global atomic per channel per block.
+// vectorised column sums for ld % 8 == 0: grid (row blocks, column blocks of <= 2048 channels); a block owns
+// a contiguous row range, thread -> (8-channel vector, row lane), fp32 partials in registers over the whole
+// range with 4 independent 16-byte loads in flight, then shared atomics and one global atomic per channel.
 __global__ void __launch_bounds__(256) og_colsum_vec_kernel(const uint4* __restrict__ x, long long rows, int C, int ld,
-                                                            float* __restrict__ out) {
-  extern __shared__ float sh[];  // [ld]
-  const int cvs = ld >> 3;
-  for (int i = threadIdx.x; i < ld; i += 256) sh[i] = 0.f;
+                                                            long long rows_per_block, float* __restrict__ out) {
+  extern __shared__ float sh[];  // [cw]
+  const int c0 = blockIdx.y * 2048;
+  const int cw = (ld - c0 < 2048) ? ld - c0 : 2048;  // columns of this block
+  const int cvs = cw >> 3, ldv = ld >> 3;
+  for (int i = threadIdx.x; i < cw; i += 256) sh[i] = 0.f;
   __syncthreads();
-  const int lanes = 256 / cvs;  // row lanes per block (cvs <= 256)
+  const int lanes = 256 / cvs;
   const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
-  if (rl < lanes) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long rend = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  if (rl < lanes && r0 < rows) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long rows_per_block = 1024;
-    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const uint4* base = x + (c0 >> 3) + cv;
     long long r = r0 + rl;
-    const long long rend = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
     for (; r + 3LL * lanes < rend; r += 4LL * lanes) {
       uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(x + (r + (long long)k * lanes) * cvs + cv);
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(base + (r + (long long)k * lanes) * ldv);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(256) og_colsum_vec_kernel(const uint4* __restr
       }
     }
     for (; r < rend; r += lanes) {
-      const uint4 u = __ldg(x + r * cvs + cv);
+      const uint4 u = __ldg(base + r * ldv);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -289,7 +292,8 @@ __global__ void __launch_bounds__(256) og_colsum_vec_kernel(const uint4* __restr
     for (int i = 0; i < 8; ++i) atomicAdd(&sh[cv * 8 + i], acc[i]);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) atomicAdd(&out[c], sh[c]);
+  for (int c = threadIdx.x; c < cw; c += 256)
+    if (c0 + c < C) atomicAdd(&out[c0 + c], sh[c]);
 }
 
 // copy [rows][cs] -> [rows][cd] (cd >= cs zero padded, or cd < cs truncating); src f32 or bf16, dst bf16
@@ -443,9 +447,16 @@ extern "C" int og_mse_bwd(const float* rec_ndhwc, const float* tgt_ncdhw, const 
 
 extern "C" int og_colsum(const void* x, int64_t rows, int C, int ld, float* out, og_stream_t stream) {
   OG_REQUIRE(x && out && C > 0 && ld >= C, "colsum: bad arguments");
-  if (ld % 8 == 0 && ld <= 2048 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    const unsigned blocks = (unsigned)((rows + 1023) / 1024);
-    og_colsum_vec_kernel<<<blocks, 256, ld * sizeof(float), (cudaStream_t)stream>>>((const uint4*)x, rows, C, ld, out);
+  if (ld % 8 == 0 && (ld <= 2048 || ld % 2048 == 0) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int col_blocks = (ld + 2047) / 2048;
+    long long want = (4LL * num_sms() + col_blocks - 1) / col_blocks;
+    long long groups = (rows + 63) / 64;
+    if (want > groups) want = groups;
+    if (want < 1) want = 1;
+    const long long rpb = ((groups + want - 1) / want) * 64;
+    dim3 grid((unsigned)((rows + rpb - 1) / rpb), col_blocks);
+    const int cw = ld < 2048 ? ld : 2048;
+    og_colsum_vec_kernel<<<grid, 256, cw * sizeof(float), (cudaStream_t)stream>>>((const uint4*)x, rows, C, ld, rpb, out);
   } else {
     const unsigned blocks = (unsigned)((rows + 255) / 256);
     og_colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, ld, out);

@@ -45,57 +45,53 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 // statistics: grid (chunks, N); block 256. Thread -> (channel vector cv, row lane rl).
 // ------------------------------------------------------------------------------------------------
-static constexpr int kStatRows = 256;  // voxel rows per block
+static constexpr int kStatRows = 256;  // granularity of the row ranges handed to a block
 
+// grid (blocks_per_sample, N); each block owns a contiguous row range of one sample and keeps fp32 partial
+// sums in registers over the whole range (4 independent 16-byte loads in flight per thread), then one
+// shared-memory and one global fp64 atomic per group.
 __global__ void __launch_bounds__(256) og_gn_stats_kernel(const uint4* __restrict__ x, long long V, int C, int G,
-                                                          double* __restrict__ sums) {
-  const int cvs = C >> 3;  // channel vectors per row
+                                                          long long rows_per_block, double* __restrict__ sums) {
+  const int cvs = C >> 3;  // channel vectors per row (host guarantees cvs <= 256)
   const int n = blockIdx.y;
-  const long long row0 = (long long)blockIdx.x * kStatRows;
-  const int rows_per_pass = 256 / cvs > 0 ? 256 / cvs : 1;
-  __shared__ double sh[64 * 2];  // up to 64 groups
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = (r_begin + rows_per_block < V) ? r_begin + rows_per_block : V;
+  __shared__ double sh[64 * 2];
   for (int i = threadIdx.x; i < 2 * G; i += 256) sh[i] = 0.0;
   __syncthreads();
-  if (cvs <= 256) {
-    const int cv = threadIdx.x % cvs;
-    const int rl = threadIdx.x / cvs;
-    if (rl < rows_per_pass) {
-      float s = 0.f, ss = 0.f;
-      for (int r = rl; r < kStatRows; r += rows_per_pass) {
-        const long long row = row0 + r;
-        if (row >= V) break;
-        const uint4 u = __ldg(x + ((long long)n * V + row) * cvs + cv);
+  const int lanes = 256 / cvs;
+  const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
+  if (rl < lanes && r_begin < V) {
+    const uint4* base = x + (long long)n * V * cvs + cv;
+    float s = 0.f, ss = 0.f;
+    long long r = r_begin + rl;
+    for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(base + (r + (long long)k * lanes) * cvs);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
         float f[8];
-        unpack8(u, f);
+        unpack8(u[k], f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           s += f[i];
-          ss += f[i] * f[i];
+          ss = fmaf(f[i], f[i], ss);
         }
       }
-      const int g = (cv * 8) / (C / G);
-      atomicAdd(&sh[2 * g], (double)s);
-      atomicAdd(&sh[2 * g + 1], (double)ss);
     }
-  } else {
-    for (int cv = threadIdx.x; cv < cvs; cv += 256) {
-      float s = 0.f, ss = 0.f;
-      for (int r = 0; r < kStatRows; ++r) {
-        const long long row = row0 + r;
-        if (row >= V) break;
-        const uint4 u = __ldg(x + ((long long)n * V + row) * cvs + cv);
-        float f[8];
-        unpack8(u, f);
+    for (; r < r_end; r += lanes) {
+      float f[8];
+      unpack8(__ldg(base + r * cvs), f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s += f[i];
-          ss += f[i] * f[i];
-        }
+      for (int i = 0; i < 8; ++i) {
+        s += f[i];
+        ss = fmaf(f[i], f[i], ss);
       }
-      const int g = (cv * 8) / (C / G);
-      atomicAdd(&sh[2 * g], (double)s);
-      atomicAdd(&sh[2 * g + 1], (double)ss);
     }
+    const int g = (cv * 8) / (C / G);
+    atomicAdd(&sh[2 * g], (double)s);
+    atomicAdd(&sh[2 * g + 1], (double)ss);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&sums[(long long)n * G * 2 + i], sh[i]);
@@ -168,17 +164,17 @@ __global__ void __launch_bounds__(256) og_affine_act_fwd_kernel(const uint4* __r
 __global__ void __launch_bounds__(256)
     og_affine_act_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                     const float* __restrict__ A, const float* __restrict__ B, long long V, int C,
-                                    int act, float* __restrict__ S) {
-  const int cvs = C >> 3;
+                                    int act, long long rows_per_block, float* __restrict__ S) {
+  const int cvs = C >> 3;  // host guarantees cvs <= 256
   const int n = blockIdx.y;
-  const long long row0 = (long long)blockIdx.x * kStatRows;
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = (r_begin + rows_per_block < V) ? r_begin + rows_per_block : V;
   extern __shared__ float shs[];  // [C][2]
   for (int i = threadIdx.x; i < 2 * C; i += 256) shs[i] = 0.f;
   __syncthreads();
-  const int rows_per_pass = (cvs <= 256) ? 256 / cvs : 1;
-  for (int cv = threadIdx.x % (cvs < 256 ? cvs : 256); cv < cvs; cv += 256) {
-    const int rl = (cvs <= 256) ? threadIdx.x / cvs : 0;
-    if (rl >= rows_per_pass) break;
+  const int lanes = 256 / cvs;
+  const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
+  if (rl < lanes && r_begin < V) {
     float av[8], bv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -186,13 +182,33 @@ __global__ void __launch_bounds__(256)
       bv[k] = B[(long long)n * C + cv * 8 + k];
     }
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int r = rl; r < kStatRows; r += rows_per_pass) {
-      const long long row = row0 + r;
-      if (row >= V) break;
-      const long long i = ((long long)n * V + row) * cvs + cv;
+    const long long base = (long long)n * V * cvs + cv;
+    long long r = r_begin + rl;
+    for (; r + (long long)lanes < r_end; r += 2LL * lanes) {
+      const uint4 ux0 = __ldg(x + base + r * cvs), ud0 = __ldg(dy + base + r * cvs);
+      const uint4 ux1 = __ldg(x + base + (r + lanes) * cvs), ud1 = __ldg(dy + base + (r + lanes) * cvs);
       float fx[8], fd[8];
-      unpack8(__ldg(x + i), fx);
-      unpack8(__ldg(dy + i), fd);
+      unpack8(ux0, fx);
+      unpack8(ud0, fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
+        s1[k] += dpre;
+        s2[k] = fmaf(dpre, fx[k], s2[k]);
+      }
+      unpack8(ux1, fx);
+      unpack8(ud1, fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
+        s1[k] += dpre;
+        s2[k] = fmaf(dpre, fx[k], s2[k]);
+      }
+    }
+    for (; r < r_end; r += lanes) {
+      float fx[8], fd[8];
+      unpack8(__ldg(x + base + r * cvs), fx);
+      unpack8(__ldg(dy + base + r * cvs), fd);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
@@ -283,6 +299,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// (blocks_per_sample, N) grid of ~4 blocks per SM; every block owns a contiguous range of whole
+// kStatRows-row groups of one sample.
+static dim3 reduce_grid(int N, long long V, long long* rows_per_block) {
+  long long groups = (V + kStatRows - 1) / kStatRows;
+  long long want = (4LL * num_sms() + N - 1) / N;
+  if (want < 1) want = 1;
+  if (want > groups) want = groups;
+  const long long gpb = (groups + want - 1) / want;
+  *rows_per_block = gpb * kStatRows;
+  return dim3((unsigned)((groups + gpb - 1) / gpb), (unsigned)N);
+}
+
 static int ew_grid(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = (long long)num_sms() * 16;
@@ -299,8 +327,10 @@ extern "C" int og_gn_stats(const void* x, int N, int64_t V, int C, int G, double
   OG_REQUIRE(x && sums, "gn_stats: null pointer");
   OG_REQUIRE(C % 8 == 0 && G >= 1 && G <= 64 && C % G == 0 && (C / G) % 8 == 0,
              "gn_stats: need C%%8==0, G<=64, (C/G)%%8==0 (C=%d G=%d)", C, G);
-  dim3 grid((unsigned)((V + kStatRows - 1) / kStatRows), N);
-  og_gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), V, C, G, sums);
+  OG_REQUIRE(C <= 2048, "gn_stats: C=%d > 2048", C);
+  long long rpb;
+  const dim3 grid = reduce_grid(N, V, &rpb);
+  og_gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), V, C, G, rpb, sums);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;
@@ -334,10 +364,11 @@ extern "C" int og_affine_act_fwd(const void* x, const float* A, const float* B, 
 extern "C" int og_affine_act_bwd_reduce(const void* dy, const void* x, const float* A, const float* B, int act,
                                         float* S, int N, int64_t V, int C, og_stream_t stream) {
   OG_REQUIRE(dy && x && A && B && S, "affine_act_bwd_reduce: null pointer");
-  OG_REQUIRE(C % 8 == 0 && C <= 4096, "affine_act_bwd_reduce: C=%d must be a multiple of 8 and <= 4096", C);
-  dim3 grid((unsigned)((V + kStatRows - 1) / kStatRows), N);
+  OG_REQUIRE(C % 8 == 0 && C <= 2048, "affine_act_bwd_reduce: C=%d must be a multiple of 8 and <= 2048", C);
+  long long rpb;
+  const dim3 grid = reduce_grid(N, V, &rpb);
   og_affine_act_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, V, C, act, S);
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, V, C, act, rpb, S);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;

@@ -23,6 +23,20 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_WS = {}
+
+
+def _workspace(dev, nbytes: int):
+    """Reusable fp32 scratch for split-K convolutions (small T*H*W, deep K). One buffer per device; every use
+    is stream-ordered (memset -> partial sums -> finish pass inside one og_conv3d_* call)."""
+    nbytes = min(max(nbytes, 1 << 20), 1 << 30)
+    t = _WS.get(dev)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WS[dev] = t
+    return t
+
+
 # Optional per-launch timing of the tensor-core kernels (bench.py's roofline): when PROFILE is a list, every
 # conv launch appends (kind, flops, start_event, end_event). CUDA events on the launching stream; no syncs.
 PROFILE = None
@@ -179,6 +193,7 @@ class _Conv3dFn(torch.autograd.Function):
         To, Ho, Wo = geom.out_dims(T, H, W)
         y = empty_internal(B, geom.cout, To, Ho, Wo, f32 if out_f32 else bf16, x.device)
         ldw = packed.shape[1]
+        ws = _workspace(x.device, B * To * Ho * Wo * geom.cout * 4)
         x2i = None
         col = None
         if geom.direct:
@@ -189,7 +204,7 @@ class _Conv3dFn(torch.autograd.Function):
             _conv_call('fwd', 2.0 * B * T * H * W * geom.cout * (geom.k_main + c1),
                        'og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
                       _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), y.data_ptr(), int(out_f32),
-                      B, T, H, W, geom.cout, s)
+                      B, T, H, W, geom.cout, ws.data_ptr(), ws.numel(), s)
         else:
             assert x2 is None
             col = torch.empty((B * To * Ho * Wo, geom.kpad), dtype=bf16, device=x.device)
@@ -197,7 +212,8 @@ class _Conv3dFn(torch.autograd.Function):
                       geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
             _conv_call('fwd', 2.0 * B * To * Ho * Wo * geom.cout * geom.k_main,
                        'og_conv3d_fwd', col.data_ptr(), geom.kpad, 1, 1, 1, 0, 0, 0, None, 0, packed.data_ptr(), ldw,
-                      _ptr(bias), None, y.data_ptr(), int(out_f32), 1, 1, 1, B * To * Ho * Wo, geom.cout, s)
+                      _ptr(bias), None, y.data_ptr(), int(out_f32), 1, 1, 1, B * To * Ho * Wo, geom.cout,
+                      ws.data_ptr(), ws.numel(), s)
         ctx.geom = geom
         ctx.in_shape = (B, C, T, H, W)
         ctx.has_bias = (bias is not None, bias2 is not None)
@@ -219,6 +235,7 @@ class _Conv3dFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         dx = dw = db = dx2 = dw2 = db2 = None
         dev = dy.device
+        ws = _workspace(dev, B * T * H * W * max(C, 64) * 4)
 
         def wgrad(xin, cin, kt, kh, kw, pt, ph, pw, shape5, dims):
             """fp32 gradient with the parameter's channels_last_3d memory: [cout][tap][cin]."""
@@ -234,7 +251,7 @@ class _Conv3dFn(torch.autograd.Function):
                 dx = empty_internal(B, C, T, H, W, bf16, dev)
                 _conv_call('dgrad', 2.0 * B * T * H * W * cout * geom.k_main,
                            'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, geom.kt, geom.kh,
-                           geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, s)
+                           geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, ws.data_ptr(), ws.numel(), s)
             if need[1]:
                 g = wgrad(xs, C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, ctx.w_shapes[0], (B, T, H, W))
                 dw = g.view(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
@@ -244,7 +261,7 @@ class _Conv3dFn(torch.autograd.Function):
                     dx2 = empty_internal(B, c1, T, H, W, bf16, dev)
                     _conv_call('dgrad', 2.0 * B * T * H * W * cout * c1,
                                'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, geom.k_main,
-                               1, 1, 1, 0, 0, 0, dx2.data_ptr(), 0, B, T, H, W, c1, s)
+                               1, 1, 1, 0, 0, 0, dx2.data_ptr(), 0, B, T, H, W, c1, ws.data_ptr(), ws.numel(), s)
                 if need[4]:
                     g = wgrad(x2i, c1, 1, 1, 1, 0, 0, 0, ctx.w_shapes[1], (B, T, H, W))
                     dw2 = g.view(cout, 1, 1, 1, c1).permute(0, 4, 1, 2, 3)
@@ -254,7 +271,7 @@ class _Conv3dFn(torch.autograd.Function):
                 dcol = torch.empty_like(col)
                 _conv_call('dgrad', 2.0 * B * To * Ho * Wo * cout * geom.k_main,
                            'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, 1, 1, 1, 0, 0, 0,
-                           dcol.data_ptr(), 0, 1, 1, 1, B * To * Ho * Wo, geom.kpad, s)
+                           dcol.data_ptr(), 0, 1, 1, 1, B * To * Ho * Wo, geom.kpad, None, 0, s)
                 dx = empty_internal(B, C, T, H, W, bf16, dev)
                 _lib.call('og_col2im3d', dcol.data_ptr(), dx.data_ptr(), 0, B, T, H, W, C, geom.kt, geom.kh, geom.kw,
                           geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
