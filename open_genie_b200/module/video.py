@@ -85,6 +85,10 @@ class Conv3dParams(nn.Module):
         return self.packed(), 0
 
     def forward(self, x: Tensor, x2: Tensor | None = None, out_f32: bool = False) -> Tensor:
+        ops._require_cuda(x, 'conv input')
+        if not self.weight.is_cuda:
+            raise RuntimeError('open_genie_b200: module parameters must be on a CUDA device (no CPU path); '
+                               'call .cuda() / .to("cuda") first')
         e = self._extra
         assert (x2 is None) or (e is not None), 'second input given but no fused shortcut registered'
         if e is not None and x2 is not None:
