@@ -59,12 +59,15 @@ uint64_t og_launch_count(void);
  * x0: bf16 [N,T,H,W,c0], c0 % 64 == 0.  x1: bf16 [N,T,H,W,c1] or NULL (c1 % 64 == 0).
  * w : bf16 [cout][ldw], ldw >= kt*kh*kw*c0 + c1, ldw % 8 == 0.
  * out: [N,T,H,W,cout], bf16 or fp32 (out_f32 != 0). bias0/bias1: fp32 [cout] or NULL.
+ * residual: optional bf16 [N,T,H,W,cout] added in fp32 before the output rounding (the `ffn(x) + x` skip of
+ * SpaceTimeAttention, attention.py:472).
  * Reads outside [0,T)x[0,H)x[0,W) are zero (pad_mode='constant').
  * workspace (optional, may be NULL): N*T*H*W*cout fp32 of scratch enables split-K for problems whose tiles
  * cannot fill the 148 SMs (small T*H*W, deep K); without it the same result is computed unsplit. */
 int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1, int c1,
-                  const void* w, int ldw, const float* bias0, const float* bias1, void* out, int out_f32, int N,
-                  int T, int H, int W, int cout, void* workspace, size_t workspace_bytes, og_stream_t stream);
+                  const void* w, int ldw, const float* bias0, const float* bias1, const void* residual, void* out,
+                  int out_f32, int N, int T, int H, int W, int cout, void* workspace, size_t workspace_bytes,
+                  og_stream_t stream);
 
 /* Data gradient of the same convolution (autograd's conv3d backward-input, reached from
  * video.py:192 / 609-629 / 599-603 during loss.backward()).
@@ -158,6 +161,9 @@ int og_colsum(const void* x, int64_t rows, int C, int ld, float* out, og_stream_
 /* y[row][0:cd] = x[row][0:cs] zero-padded / truncated; x fp32 or bf16, y bf16. */
 int og_pad_channels(const void* x, int x_f32, void* y, int64_t rows, int cs, int cd, og_stream_t stream);
 
+/* out = a - b on n bf16 elements (n % 8 == 0). */
+int og_sub_rows(const void* a, const void* b, void* out, int64_t n, og_stream_t stream);
+
 /* dst[row*dst_ld + c] = bf16(src[row*src_ld + c]) for c < cols: refreshes the bf16 operand copy of a
  * conv weight (the cast torch.autocast performs on every conv call, config/tokenize.yaml:78) into one
  * segment of a packed [cout][ldw] weight matrix. src: fp32 or bf16. */
@@ -184,6 +190,43 @@ int og_lfq_fwd(const float* x, int ldx, int64_t ntok, int D, float beta, int tra
 int og_lfq_bwd(const float* x, int ldx, int64_t ntok, int D, float beta, float w_commit, float w_entropy,
                const float* gloss, const float* dout, int ld_dout, float* dx_f32, void* dx_bf16, int ld_dx,
                void* workspace, og_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * factored space-time attention (genie/module/attention.py)
+ * All tensors are NDHWC rows [B*T*H*W][C] bf16; a spatial sequence is the H*W rows of one frame, a
+ * temporal sequence the T rows of one pixel (stride H*W rows) — no transposition copies.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y = LayerNorm(RoPE(x)): RotaryEmbedding.forward/apply (attention.py:48-94: interleaved pairs over the full
+ * channel dim, fp32 angle = pos * freq[i]) followed by nn.LayerNorm (attention.py:219-220).
+ * pos(row) = (row / pos_div) % pos_mod — spatial: (1, H*W); temporal: (H*W, T). freq: fp32 [C/2]. */
+int og_rope_ln_fwd(const void* x, const float* freq, const float* gamma, const float* beta, float eps, void* y,
+                   int64_t rows, int C, int64_t pos_div, int pos_mod, og_stream_t stream);
+/* dx = RoPE^T(LN'(g0 + g1 + g2)) + add ; dgamma/dbeta accumulated (+=). g1, g2, add may be NULL. */
+int og_rope_ln_bwd(const void* x, const float* freq, const float* gamma, float eps, const void* g0, const void* g1,
+                   const void* g2, const void* add, void* dx, float* dgamma, float* dbeta, int64_t rows, int C,
+                   int64_t pos_div, int pos_mod, og_stream_t stream);
+
+/* Spatial attention: F.scaled_dot_product_attention(q,k,v, scale) non-causal (attention.py:229-234) on
+ * tcgen05 tensor cores. q,k,v,out: [nseq][S][C], C = n_head*64. lse: fp32 [nseq][n_head][S] (saved for backward).
+ * residual / out_res (optional, bf16 like out): out_res = out + residual, i.e. `attn(x) + skip(x)`
+ * (attention.py:470-471), added in fp32; `out` itself is still written (the backward pass needs it). */
+int og_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, const void* residual, void* out_res,
+                      float* lse, int nseq, int S, int C, int n_head, float scale, og_stream_t stream);
+/* delta_ws: fp32 [nseq][n_head][S] scratch. dq, dk, dv: bf16 [nseq][S][C]. */
+int og_flash_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                      const float* lse, float* delta_ws, void* dq, void* dk, void* dv, int nseq, int S, int C,
+                      int n_head, float scale, og_stream_t stream);
+
+/* Temporal attention, is_causal=True (attention.py:347-371, 423): one sequence per (batch, pixel), T <= 32.
+ * q/out rows ((b*T + t)*P + p); k,v either the same layout (kv_bcast=0) or [B][T][C] shared by all pixels
+ * (kv_bcast=1: latent-action conditioning through to_k/to_v, attention.py:127-129,362-363). */
+int og_temporal_attn_fwd(const void* q, const void* k, const void* v, const void* residual, void* out, int B, int T,
+                         int64_t P, int C, int n_head, float scale, int kv_bcast, og_stream_t stream);
+/* kv_bcast=0: dk, dv bf16 like k, v. kv_bcast=1: dk_bcast, dv_bcast fp32 [B][T][C], ACCUMULATED (+=). */
+int og_temporal_attn_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
+                         float* dk_bcast, float* dv_bcast, int B, int T, int64_t P, int C, int n_head, float scale,
+                         int kv_bcast, og_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fused multi-tensor AdamW (genie/tokenizer.py:437-442) + bf16 operand refresh

@@ -54,6 +54,7 @@ struct IgemmParams {
   int num_kb;  // k-blocks per tile
   int m_sub;   // M sub-tiles (of 128 rows) per CTA tile sharing one B stage: 1 or 2
   int fast_store;  // bf16 output, n_out % 64 == 0, block_n % 64 == 0: coalesced staged stores
+  const __nv_bfloat16* residual;  // optional bf16 [voxels][n_out] added to the output (out = conv + bias + residual)
   int splits;      // split-K factor (1 = none): each work item covers a k-block range and reduces into `ws`
   float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zeroed by the launcher) when splits > 1
 };
@@ -316,6 +317,21 @@ __global__ void __launch_bounds__(kThreads, 1)
           tmem_ld_32x32(t_addr + c, v0);
           tmem_ld_32x32(t_addr + c + 32, v1);
           tmem_ld_wait();
+          if (p.residual && row_ok) {  // fp32 add before the single bf16 rounding
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + vox * p.ldo + col0 + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 u = __ldg(rp + j);
+              const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(hh[e]);
+                uint32_t* dst = (j < 4) ? &v0[8 * j + 2 * e] : &v1[8 * (j - 4) + 2 * e];
+                dst[0] = __float_as_uint(__uint_as_float(dst[0]) + f.x);
+                dst[1] = __float_as_uint(__uint_as_float(dst[1]) + f.y);
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -374,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (p.bias1) b += __ldg(p.bias1 + col);
           }
           f[j] = __uint_as_float(v[j]) + b;
+          if (p.residual && col < p.n_out && row_ok) f[j] += __bfloat162float(p.residual[vox * p.ldo + col]);
         }
         if (p.out_f32) {
           float* o = reinterpret_cast<float*>(p.out) + vox * p.ldo + cbase;
@@ -453,8 +470,9 @@ static int pick_block_n(int n_out, int num_m_tiles, bool mn_major) {
 
 static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const IgemmSeg* segs, int nseg, int sgn,
                         const void* w, int ldw, int k_off, int b_mn_major, int b_rows /*K rows for MN-major*/,
-                        int b_ntaps, const float* bias0, const float* bias1, void* out, int out_f32, int N, int T,
-                        int H, int W, int n_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                        int b_ntaps, const float* bias0, const float* bias1, const void* residual, void* out,
+                        int out_f32, int N, int T, int H, int W, int n_out, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
   OG_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0 && n_out > 0, "conv3d: empty problem");
   int bw, bh, bt, bn;
   choose_voxel_box(kBlockM, N, T, H, W, &bw, &bh, &bt, &bn);
@@ -493,6 +511,7 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   p.vec_ok = out_f32 ? (n_out % 4 == 0) : (n_out % 8 == 0);
   p.bias0 = bias0;
   p.bias1 = bias1;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   // TMA latency x smem capacity bounds the bytes/clk one SM can stream; sharing each B stage between two
   // 128-row M sub-tiles keeps the demand at (32+16) KB per 512 MMA-clk (same as a 128x256 tile).
   p.m_sub = (p.block_n <= 128 && p.num_m_tiles >= 2 * num_sms()) ? 2 : 1;
@@ -508,7 +527,7 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   {
     const long long tiles = (long long)((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles;
     const size_t need = (size_t)N * T * H * W * n_out * sizeof(float);
-    if (tiles * 2 <= num_sms() && p.num_kb >= 32 && workspace && workspace_bytes >= need) {
+    if (tiles * 2 <= num_sms() && p.num_kb >= 32 && workspace && workspace_bytes >= need && !residual) {
       int sp = (int)(num_sms() / tiles);
       if (sp > p.num_kb / 8) sp = p.num_kb / 8;
       if (sp > 16) sp = 16;
@@ -585,9 +604,9 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
 }  // namespace og
 
 extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1,
-                             int c1, const void* w, int ldw, const float* bias0, const float* bias1, void* out,
-                             int out_f32, int N, int T, int H, int W, int cout, void* workspace, size_t workspace_bytes,
-                             og_stream_t stream) {
+                             int c1, const void* w, int ldw, const float* bias0, const float* bias1,
+                             const void* residual, void* out, int out_f32, int N, int T, int H, int W, int cout,
+                             void* workspace, size_t workspace_bytes, og_stream_t stream) {
   using namespace og;
   OG_REQUIRE(x0 && w && out, "conv3d_fwd: null pointer");
   OG_REQUIRE(c0 > 0 && c0 % 64 == 0, "conv3d_fwd: c0=%d must be a positive multiple of 64 (use the im2col path)", c0);
@@ -599,8 +618,8 @@ extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int
   IgemmSeg segs[2];
   segs[0] = IgemmSeg{c0 / 64, kt, kh, kw, pt, ph, pw};
   segs[1] = IgemmSeg{c1 / 64, 1, 1, 1, 0, 0, 0};
-  return launch_igemm(x0, c0, x1, c1, segs, x1 ? 2 : 1, +1, w, ldw, 0, 0, 0, 0, bias0, bias1, out, out_f32, N, T, H, W,
-                      cout, workspace, workspace_bytes, (cudaStream_t)stream);
+  return launch_igemm(x0, c0, x1, c1, segs, x1 ? 2 : 1, +1, w, ldw, 0, 0, 0, 0, bias0, bias1, residual, out, out_f32, N, T,
+                      H, W, cout, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int k_off, int kt, int kh,
@@ -614,6 +633,6 @@ extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void*
   OG_REQUIRE(w_rows > 0 && w_rows <= cout, "conv3d_dgrad: w_rows=%d must be in (0, cout]", w_rows);
   IgemmSeg segs[1];
   segs[0] = IgemmSeg{cout / 64, kt, kh, kw, pt, ph, pw};
-  return launch_igemm(dy, cout, nullptr, 0, segs, 1, -1, w, ldw, k_off, 1, w_rows, kt * kh * kw, nullptr, nullptr, dx,
+  return launch_igemm(dy, cout, nullptr, 0, segs, 1, -1, w, ldw, k_off, 1, w_rows, kt * kh * kw, nullptr, nullptr, nullptr, dx,
                       dx_f32, N, T, H, W, cin, workspace, workspace_bytes, (cudaStream_t)stream);
 }

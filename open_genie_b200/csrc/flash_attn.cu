@@ -1,0 +1,626 @@
+// flash_attn.cu — spatial (non-causal) multi-head attention, FlashAttention-style, on tcgen05 tensor cores.
+//
+// Reference: F.scaled_dot_product_attention(q, k, v, scale = n_head * d_head**-0.5) reached from
+// SpatialAttention.forward -> Attention.forward (genie/module/attention.py:279-307, 199-239), with
+// q = k = v = LayerNorm(RoPE(x)) in the HEAD-valid configuration. Layout: [nseq][S][C] bf16 rows
+// (one sequence = the H*W tokens of one frame, contiguous in NDHWC), head h = columns [h*64, h*64+64).
+//
+// Forward, one CTA per (sequence, head, 128-query tile), loop over 128-key tiles:
+//   S  = Q K^T           tcgen05.mma, A = Q tile (K-major), B = K tile (K-major)      -> TMEM [128][128] fp32
+//   P  = exp(S*scale - m) softmax warps: one TMEM lane (= query row) per thread, online max / sum in registers,
+//                         P written as bf16 into a 128-byte-swizzled smem tile (the A operand of the next MMA)
+//   PV = P V             tcgen05.mma, A = P (K-major, smem), B = V tile (MN-major: keys are the K dim)
+//   O  = O*alpha + PV    in registers (64 fp32 per thread)
+// Q/K/V tiles arrive by 3-D TMA (rows beyond S are zero-filled and masked to -inf).
+// Backward recomputes P from the saved log-sum-exp and accumulates dK/dV in TMEM per key tile, dQ via
+// fp32 reductions (see og_flash_attn_bwd_kernel).
+#include "og_host.cuh"
+#include "og_ptx.cuh"
+
+namespace og {
+extern std::atomic<uint64_t> g_launches;
+
+static constexpr int kD = 64;            // head dim
+static constexpr int kTile = 128;        // queries / keys per tile
+static constexpr int kTileBytes = kTile * kD * 2;  // 16 KiB
+static constexpr int kFaThreads = 192;
+
+struct FaParams {
+  int S, C, nh, nseq;
+  int q_tiles, kv_tiles;
+  float scale;
+  __nv_bfloat16* out;  // [nseq][S][C]
+  float* lse;          // [nseq][nh][S]
+  const __nv_bfloat16* res;  // optional residual: out_res = attn + res (x = attn(x) + x, attention.py:470)
+  __nv_bfloat16* out_res;
+};
+
+// write 8 consecutive bf16 (one 16-byte chunk) of row `row`, chunk index `chunk` (0..7) into a
+// [rows][128 B] tile with the 128-byte swizzle TMA / UMMA use (chunk ^= row & 7)
+__device__ __forceinline__ void st_swizzled_chunk(uint8_t* tile, int row, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+}
+
+__global__ void __launch_bounds__(kFaThreads, 1)
+    og_flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                             const __grid_constant__ CUtensorMap mapV, const FaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                         // 16 KiB
+  uint8_t* sKV = smem + kTileBytes;           // 2 stages x (K 16 KiB + V 16 KiB)
+  uint8_t* sP = sKV + 4 * kTileBytes;         // 2 k-blocks x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_ready = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* pv_ready = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int id = blockIdx.x;
+  const int qt = id % p.q_tiles;
+  id /= p.q_tiles;
+  const int h = id % p.nh;
+  const int seq = id / p.nh;
+  const int q0 = qt * kTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(pv_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;         // 128 columns
+  const uint32_t tPV = tmem_base + 128;  // 64 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &mapQ, q_full, h * kD, q0, seq);
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
+        tma_load_3d(sKV + st * 2 * kTileBytes, &mapK, &kv_full[st], h * kD, j * kTile, seq);
+        tma_load_3d(sKV + st * 2 * kTileBytes + kTileBytes, &mapV, &kv_full[st], h * kD, j * kTile, seq);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0u, 0u);   // S = Q K^T : both K-major
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0u, 1u);   // PV = P V  : A K-major, B MN-major
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j <= p.kv_tiles; ++j) {
+        if (j < p.kv_tiles) {
+          // S_j = Q K_j^T (issued before PV_{j-1} completes its consumer side: overlaps the softmax warps' O update)
+          const int st = j & 1;
+          mbar_wait(&kv_full[st], (j >> 1) & 1);
+          tc_fence_after();
+          if (j > 0) {
+            // S buffer is free once P_{j-1} has been written (the softmax warps are done reading S_{j-1})
+            mbar_wait(p_ready, (j - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t k_addr = smem_u32(sKV + st * 2 * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k)
+            umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(s_ready);
+        }
+        if (j > 0) {
+          // PV_{j-1} = P_{j-1} V_{j-1}
+          const int jj = j - 1, st = jj & 1;
+          if (j == p.kv_tiles) {  // otherwise already waited above
+            mbar_wait(p_ready, jj & 1);
+            tc_fence_after();
+          }
+          const uint32_t v_addr = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k)
+            umma_bf16_ss(tPV, umma_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                         umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_pv, k > 0 ? 1u : 0u);
+          umma_commit(pv_ready);
+          umma_commit(&kv_empty[st]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ softmax / output warps: thread = query row ============================
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    float o[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < p.kv_tiles; ++j) {
+      mbar_wait(s_ready, j & 1);
+      tc_fence_after();
+      const int kv_valid = p.S - j * kTile;  // keys of this tile that exist (>= 128 except for the last tile)
+      // pass 1: row max
+      float mt = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kTile; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < kv_valid) mt = fmaxf(mt, __uint_as_float(v[i]) * p.scale);
+      }
+      const float mn = fmaxf(m, mt);
+      const float alpha = __expf(m - mn);
+      // pass 2: P = exp(s - m), row sum, bf16 P -> swizzled smem
+      float ls = 0.f;
+#pragma unroll
+      for (int c = 0; c < kTile; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_addr + c, v);
+        tmem_ld_wait();
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pf[i] = (c + i < kv_valid) ? __expf(__uint_as_float(v[i]) * p.scale - mn) : 0.f;
+          ls += pf[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(pf[i], pf[i + 1]);
+          u.y = pack_bf16x2(pf[i + 2], pf[i + 3]);
+          u.z = pack_bf16x2(pf[i + 4], pf[i + 5]);
+          u.w = pack_bf16x2(pf[i + 6], pf[i + 7]);
+          const int col = c + i;
+          st_swizzled_chunk(sP + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+        }
+      }
+      l = l * alpha + ls;
+      m = mn;
+      // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      // O = O * alpha + P V
+      mbar_wait(pv_ready, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tPV + lane_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+    }
+    const int qrow = q0 + row;
+    if (qrow < p.S) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* dst = p.out + ((long long)seq * p.S + qrow) * p.C + h * kD;
+#pragma unroll
+      for (int i = 0; i < kD; ++i) o[i] *= inv;
+#pragma unroll
+      for (int i = 0; i < kD; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(o[i], o[i + 1]);
+        u.y = pack_bf16x2(o[i + 2], o[i + 3]);
+        u.z = pack_bf16x2(o[i + 4], o[i + 5]);
+        u.w = pack_bf16x2(o[i + 6], o[i + 7]);
+        *reinterpret_cast<uint4*>(dst + i) = u;
+      }
+      if (p.res) {  // second output: attention + residual, added in fp32 before the rounding
+        const long long off = ((long long)seq * p.S + qrow) * p.C + h * kD;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+        __nv_bfloat16* dst2 = p.out_res + off;
+#pragma unroll
+        for (int i = 0; i < kD; i += 8) {
+          const uint4 ur = __ldg(rp + (i >> 3));
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&ur);
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __bfloat1622float2(hh[e]);
+            f[2 * e] = o[i + 2 * e] + t.x;
+            f[2 * e + 1] = o[i + 2 * e + 1] + t.y;
+          }
+          uint4 u;
+          u.x = pack_bf16x2(f[0], f[1]);
+          u.y = pack_bf16x2(f[2], f[3]);
+          u.z = pack_bf16x2(f[4], f[5]);
+          u.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(dst2 + i) = u;
+        }
+      }
+      if (p.lse) p.lse[((long long)seq * p.nh + h) * p.S + qrow] = m + __logf(l);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// backward. Two passes over the (q tile, kv tile) pairs, both recomputing S = Q K^T and dP = dO V^T:
+//   MODE 0: one CTA per KV tile j, streams the query tiles i, accumulates in TMEM
+//             dV_j += P^T dO_i      (A = P   as MN-major operand, B = dO_i MN-major)
+//             dK_j += dS^T Q_i      (A = dS  as MN-major operand, B = Q_i  MN-major)
+//   MODE 1: one CTA per query tile i, streams the KV tiles j, accumulates
+//             dQ_i += dS K_j        (A = dS K-major, B = K_j MN-major)
+// with P = exp(S*scale - lse), dS = P * (dP - delta) * scale, delta = rowsum(dO * O).
+// No atomics, no fp32 gradient buffers; outputs are bf16 in the activation layout.
+// ------------------------------------------------------------------------------------------------
+struct FaBwdParams {
+  int S, C, nh, nseq, tiles;
+  float scale;
+  const float* lse;    // [nseq][nh][S]
+  const float* delta;  // [nseq][nh][S]
+  __nv_bfloat16* dq;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kFaThreads, 1)
+    og_flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                             const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
+                             const FaBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sFix = smem;                    // stationary pair: MODE 0: K_j, V_j ; MODE 1: Q_i, dO_i   (2 x 16 KiB)
+  uint8_t* sStr = smem + 2 * kTileBytes;   // streamed pair, 2 stages x (2 x 16 KiB)
+  uint8_t* sP = sStr + 4 * kTileBytes;     // P  bf16 [2 k-blocks][128][128 B]
+  uint8_t* sDS = sP + 2 * kTileBytes;      // dS bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kTileBytes);
+  uint64_t* fix_full = bars;
+  uint64_t* str_full = bars + 1;   // [2]
+  uint64_t* str_empty = bars + 3;  // [2]
+  uint64_t* sd_ready = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* acc_ready = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int id = blockIdx.x;
+  const int own = id % p.tiles;  // MODE 0: kv tile ; MODE 1: q tile
+  id /= p.tiles;
+  const int h = id % p.nh;
+  const int seq = id / p.nh;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    tma_prefetch_desc(&mapDO);
+    mbar_init(fix_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&str_full[s], 1);
+      mbar_init(&str_empty[s], 1);
+    }
+    mbar_init(sd_ready, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tAcc0 = tmem_base + 256, tAcc1 = tmem_base + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(fix_full, 2 * kTileBytes);
+      if (MODE == 0) {
+        tma_load_3d(sFix, &mapK, fix_full, h * kD, own * kTile, seq);
+        tma_load_3d(sFix + kTileBytes, &mapV, fix_full, h * kD, own * kTile, seq);
+      } else {
+        tma_load_3d(sFix, &mapQ, fix_full, h * kD, own * kTile, seq);
+        tma_load_3d(sFix + kTileBytes, &mapDO, fix_full, h * kD, own * kTile, seq);
+      }
+      for (int it = 0; it < p.tiles; ++it) {
+        const int st = it & 1;
+        mbar_wait(&str_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&str_full[st], 2 * kTileBytes);
+        uint8_t* d = sStr + st * 2 * kTileBytes;
+        if (MODE == 0) {
+          tma_load_3d(d, &mapQ, &str_full[st], h * kD, it * kTile, seq);
+          tma_load_3d(d + kTileBytes, &mapDO, &str_full[st], h * kD, it * kTile, seq);
+        } else {
+          tma_load_3d(d, &mapK, &str_full[st], h * kD, it * kTile, seq);
+          tma_load_3d(d + kTileBytes, &mapV, &str_full[st], h * kD, it * kTile, seq);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0u, 0u);  // S, dP: both operands K-major
+      const uint32_t idesc_mm = umma_idesc_bf16(128, 64, 1u, 1u);   // dV, dK: A (P / dS transposed) and B MN-major
+      const uint32_t idesc_km = umma_idesc_bf16(128, 64, 0u, 1u);   // dQ: A = dS K-major, B = K MN-major
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      mbar_wait(fix_full, 0);
+      for (int it = 0; it <= p.tiles; ++it) {
+        if (it < p.tiles) {
+          const int st = it & 1;
+          mbar_wait(&str_full[st], (it >> 1) & 1);
+          tc_fence_after();
+          if (it > 0) {
+            mbar_wait(p_ready, (it - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t fixa = smem_u32(sFix), stra = smem_u32(sStr + st * 2 * kTileBytes);
+          const uint32_t q_addr = MODE == 0 ? stra : fixa, do_addr = q_addr + kTileBytes;
+          const uint32_t k_addr = MODE == 0 ? fixa : stra, v_addr = k_addr + kTileBytes;
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k)
+            umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k)
+            umma_bf16_ss(tDP, umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                         umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+          umma_commit(sd_ready);
+        }
+        if (it > 0) {
+          const int jj = it - 1, st = jj & 1;
+          if (it == p.tiles) {
+            mbar_wait(p_ready, jj & 1);
+            tc_fence_after();
+          }
+          const uint32_t fixa = smem_u32(sFix), stra = smem_u32(sStr + st * 2 * kTileBytes);
+          if (MODE == 0) {
+            const uint32_t q_addr = stra, do_addr = stra + kTileBytes;
+#pragma unroll
+            for (int k = 0; k < kTile / 16; ++k) {  // K dim = 128 query rows, 16 per MMA
+              umma_bf16_ss(tAcc0, umma_smem_desc_sw128(p_addr + k * 2048, kTileBytes, 1024),
+                           umma_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_mm, (jj > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss(tAcc1, umma_smem_desc_sw128(ds_addr + k * 2048, kTileBytes, 1024),
+                           umma_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_mm, (jj > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+            const uint32_t k_addr = stra;
+#pragma unroll
+            for (int k = 0; k < kTile / 16; ++k)  // K dim = 128 keys
+              umma_bf16_ss(tAcc0, umma_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                           umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_km, (jj > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&str_empty[st]);
+          (void)fixa;
+        }
+      }
+      umma_commit(acc_ready);
+    }
+    __syncwarp();
+  } else {
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;  // TMEM lane: query row of the current pair
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    float lse_fix = 0.f, delta_fix = 0.f;
+    if (MODE == 1) {
+      const int qrow = own * kTile + row;
+      if (qrow < p.S) {
+        lse_fix = p.lse[((long long)seq * p.nh + h) * p.S + qrow];
+        delta_fix = p.delta[((long long)seq * p.nh + h) * p.S + qrow];
+      }
+    }
+    for (int it = 0; it < p.tiles; ++it) {
+      const int q_tile = MODE == 0 ? it : own, kv_tile = MODE == 0 ? own : it;
+      const int qrow = q_tile * kTile + row;
+      float lse = lse_fix, delta = delta_fix;
+      if (MODE == 0 && qrow < p.S) {
+        lse = p.lse[((long long)seq * p.nh + h) * p.S + qrow];
+        delta = p.delta[((long long)seq * p.nh + h) * p.S + qrow];
+      }
+      const bool q_ok = qrow < p.S;
+      const int kv_valid = p.S - kv_tile * kTile;
+      mbar_wait(sd_ready, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < kTile; c += 32) {
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32(tS + lane_addr + c, vs);
+        tmem_ld_32x32(tDP + lane_addr + c, vd);
+        tmem_ld_wait();
+        float pf[32], df[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool ok = q_ok && (c + i < kv_valid);
+          const float pv = ok ? __expf(__uint_as_float(vs[i]) * p.scale - lse) : 0.f;
+          pf[i] = pv;
+          df[i] = pv * (__uint_as_float(vd[i]) - delta) * p.scale;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const int col = c + i;
+          uint4 u;
+          if (MODE == 0) {
+            u.x = pack_bf16x2(pf[i], pf[i + 1]);
+            u.y = pack_bf16x2(pf[i + 2], pf[i + 3]);
+            u.z = pack_bf16x2(pf[i + 4], pf[i + 5]);
+            u.w = pack_bf16x2(pf[i + 6], pf[i + 7]);
+            st_swizzled_chunk(sP + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+          }
+          u.x = pack_bf16x2(df[i], df[i + 1]);
+          u.y = pack_bf16x2(df[i + 2], df[i + 3]);
+          u.z = pack_bf16x2(df[i + 4], df[i + 5]);
+          u.w = pack_bf16x2(df[i + 6], df[i + 7]);
+          st_swizzled_chunk(sDS + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    // accumulators complete: TMEM lane = output row (kv row in MODE 0, query row in MODE 1)
+    mbar_wait_relaxed(acc_ready, 0);
+    tc_fence_after();
+    const int orow = own * kTile + row;
+    for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
+      __nv_bfloat16* base = MODE == 1 ? p.dq : (a == 0 ? p.dv : p.dk);
+      const uint32_t tacc = a == 0 ? tAcc0 : tAcc1;
+#pragma unroll
+      for (int c = 0; c < kD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tacc + lane_addr + c, v);
+        tmem_ld_wait();
+        if (orow < p.S) {
+          __nv_bfloat16* dst = base + ((long long)seq * p.S + orow) * p.C + h * kD + c;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+            *reinterpret_cast<uint4*>(dst + i) = u;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[seq][h][s] = sum_d dO * O   (one warp per row, lanes over the head's 64 dims)
+__global__ void og_attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                     float* __restrict__ delta, long long rows, int S, int C, int nh) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long t = w0; t < rows * nh; t += nw) {
+    const int h = (int)(t % nh);
+    const long long row = t / nh;
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + row * C + h * kD + lane * 2));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(d_o + row * C + h * kD + lane * 2));
+    float v = a.x * b.x + a.y * b.y;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) delta[((row / S) * nh + h) * (long long)S + row % S] = v;
+  }
+}
+
+static int make_seq_map(CUtensorMap* m, const void* base, int nseq, int S, int C) {
+  uint64_t dims[3] = {(uint64_t)C, (uint64_t)S, (uint64_t)nseq};
+  uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)S * C * 2};
+  uint32_t box[3] = {kD, kTile, 1};
+  return make_tmap_bf16(m, base, 3, dims, str, box);
+}
+
+}  // namespace og
+
+using namespace og;
+
+extern "C" int og_flash_attn_fwd(const void* q, const void* k, const void* v, void* out, const void* residual,
+                                 void* out_res, float* lse, int nseq, int S, int C, int n_head, float scale,
+                                 og_stream_t stream) {
+  OG_REQUIRE(q && k && v && out, "flash_attn_fwd: null pointer");
+  OG_REQUIRE(n_head >= 1 && C == n_head * kD, "flash_attn_fwd: needs d_head = 64 (C=%d, n_head=%d)", C, n_head);
+  OG_REQUIRE(nseq > 0 && S > 0, "flash_attn_fwd: empty problem");
+  FaParams p;
+  p.S = S; p.C = C; p.nh = n_head; p.nseq = nseq;
+  p.q_tiles = (S + kTile - 1) / kTile;
+  p.kv_tiles = p.q_tiles;
+  p.scale = scale;
+  p.out = (__nv_bfloat16*)out;
+  p.lse = lse;
+  p.res = (const __nv_bfloat16*)residual;
+  p.out_res = (__nv_bfloat16*)out_res;
+  OG_REQUIRE(!residual || out_res, "flash_attn_fwd: residual given without out_res");
+  CUtensorMap mq, mk, mv;
+  int r;
+  if ((r = make_seq_map(&mq, q, nseq, S, C)) != OG_OK) return r;
+  if ((r = make_seq_map(&mk, k, nseq, S, C)) != OG_OK) return r;
+  if ((r = make_seq_map(&mv, v, nseq, S, C)) != OG_OK) return r;
+  const size_t smem_bytes = 7 * kTileBytes + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+    attr = true;
+  }
+  const long long grid = (long long)nseq * n_head * p.q_tiles;
+  og_flash_attn_fwd_kernel<<<(unsigned)grid, kFaThreads, smem_bytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout,
+                                 const float* lse, float* delta_ws, void* dq, void* dk, void* dv, int nseq, int S,
+                                 int C, int n_head, float scale, og_stream_t stream) {
+  OG_REQUIRE(q && k && v && out && dout && lse && delta_ws && dq && dk && dv, "flash_attn_bwd: null pointer");
+  OG_REQUIRE(n_head >= 1 && C == n_head * kD, "flash_attn_bwd: needs d_head = 64 (C=%d, n_head=%d)", C, n_head);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long rows = (long long)nseq * S;
+  {
+    long long blocks = (rows * n_head + 7) / 8;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    og_attn_delta_kernel<<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
+                                                         delta_ws, rows, S, C, n_head);
+    OG_CHECK_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+  }
+  FaBwdParams p;
+  p.S = S; p.C = C; p.nh = n_head; p.nseq = nseq;
+  p.tiles = (S + kTile - 1) / kTile;
+  p.scale = scale;
+  p.lse = lse;
+  p.delta = delta_ws;
+  p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  CUtensorMap mq, mk, mv, mdo;
+  int r;
+  if ((r = make_seq_map(&mq, q, nseq, S, C)) != OG_OK) return r;
+  if ((r = make_seq_map(&mk, k, nseq, S, C)) != OG_OK) return r;
+  if ((r = make_seq_map(&mv, v, nseq, S, C)) != OG_OK) return r;
+  if ((r = make_seq_map(&mdo, dout, nseq, S, C)) != OG_OK) return r;
+  const size_t smem_bytes = 10 * kTileBytes + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+    attr = true;
+  }
+  const long long grid = (long long)nseq * n_head * p.tiles;
+  og_flash_attn_bwd_kernel<0><<<(unsigned)grid, kFaThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+  OG_CHECK_CUDA(cudaGetLastError());
+  og_flash_attn_bwd_kernel<1><<<(unsigned)grid, kFaThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  return OG_OK;
+}

@@ -332,9 +332,37 @@ __global__ void og_copy_rows_kernel(const InT* __restrict__ src, long long src_l
   }
 }
 
+// out = a - b (bf16, 8 elements per thread): recovers the attention output o = y - x from the saved block output
+__global__ void og_sub_rows_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                   long long nvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 ua = __ldg(a + i), ub = __ldg(b + i);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+    uint4 r;
+    uint32_t* rw = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __bfloat1622float2(ha[k]), fb = __bfloat1622float2(hb[k]);
+      rw[k] = pack_bf16x2(fa.x - fb.x, fa.y - fb.y);
+    }
+    out[i] = r;
+  }
+}
+
 }  // namespace og
 
 using namespace og;
+
+extern "C" int og_sub_rows(const void* a, const void* b, void* out, int64_t n, og_stream_t stream) {
+  OG_REQUIRE(a && b && out && n > 0 && n % 8 == 0, "sub_rows: bad arguments (n must be a multiple of 8)");
+  og_sub_rows_kernel<<<ew_blocks(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b,
+                                                                             (uint4*)out, n / 8);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
 
 extern "C" int og_copy_rows_to_bf16(const void* src, int src_f32, int64_t src_ld, void* dst, int64_t dst_ld,
                                     int64_t rows, int cols, og_stream_t stream) {

@@ -203,7 +203,7 @@ class _Conv3dFn(torch.autograd.Function):
                 c1 = x2i.shape[1]
             _conv_call('fwd', 2.0 * B * T * H * W * geom.cout * (geom.k_main + c1),
                        'og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
-                      _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), y.data_ptr(), int(out_f32),
+                      _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), None, y.data_ptr(), int(out_f32),
                       B, T, H, W, geom.cout, ws.data_ptr(), ws.numel(), s)
         else:
             assert x2 is None
@@ -212,7 +212,7 @@ class _Conv3dFn(torch.autograd.Function):
                       geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
             _conv_call('fwd', 2.0 * B * To * Ho * Wo * geom.cout * geom.k_main,
                        'og_conv3d_fwd', col.data_ptr(), geom.kpad, 1, 1, 1, 0, 0, 0, None, 0, packed.data_ptr(), ldw,
-                      _ptr(bias), None, y.data_ptr(), int(out_f32), 1, 1, 1, B * To * Ho * Wo, geom.cout,
+                      _ptr(bias), None, None, y.data_ptr(), int(out_f32), 1, 1, 1, B * To * Ho * Wo, geom.cout,
                       ws.data_ptr(), ws.numel(), s)
         ctx.geom = geom
         ctx.in_shape = (B, C, T, H, W)
@@ -490,3 +490,187 @@ class _LfqFn(torch.autograd.Function):
 
 def lfq(x2d, D, beta, training, w_commit, w_entropy, w_div):
     return _LfqFn.apply(x2d, D, float(beta), bool(training), float(w_commit), float(w_entropy), float(w_div))
+
+
+# ------------------------------------------------------------------------------------------------
+# factored space-time attention (tensors here are plain contiguous (B, T, H, W, C) bf16 == NDHWC rows)
+# ------------------------------------------------------------------------------------------------
+def _rows_bf16(x: Tensor) -> Tensor:
+    """(B,T,H,W,C) contiguous bf16 view of a tensor in either logical layout (no copy when already internal)."""
+    if x.dtype != bf16 or not x.is_contiguous():
+        x = x.to(bf16).contiguous()
+    return x
+
+
+class _SpaceAttnFn(torch.autograd.Function):
+    """y = SDPA(q, q, q; scale) + x with q = LayerNorm(RoPE2d(x)), sequences = frames (H*W tokens).
+    SpatialAttention.forward + the residual of SpaceTimeAttention.forward (attention.py:279-307, 470)."""
+
+    @staticmethod
+    def forward(ctx, x, freq, gamma, beta, n_head: int, scale: float, eps: float):
+        _require_cuda(x, 'attention input')
+        x = _rows_bf16(x)
+        B, T, H, W, C = x.shape
+        rows, S = B * T * H * W, H * W
+        s = _stream()
+        q = torch.empty_like(x)
+        _lib.call('og_rope_ln_fwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
+                  q.data_ptr(), rows, C, 1, S, s)
+        y, o = torch.empty_like(x), torch.empty_like(x)
+        lse = torch.empty((B * T, n_head, S), dtype=f32, device=x.device)
+        _lib.call('og_flash_attn_fwd', q.data_ptr(), q.data_ptr(), q.data_ptr(), o.data_ptr(), x.data_ptr(),
+                  y.data_ptr(), lse.data_ptr(), B * T, S, C, n_head, scale, s)
+        ctx.cfg = (n_head, scale, eps)
+        ctx.save_for_backward(x, q, o, lse, freq, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, q, o, lse, freq, gamma = ctx.saved_tensors
+        n_head, scale, eps = ctx.cfg
+        B, T, H, W, C = x.shape
+        rows, S = B * T * H * W, H * W
+        s = _stream()
+        dy = _rows_bf16(dy)
+        dq, dk, dv = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        delta = torch.empty_like(lse)
+        _lib.call('og_flash_attn_bwd', q.data_ptr(), q.data_ptr(), q.data_ptr(), o.data_ptr(), dy.data_ptr(),
+                  lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B * T, S, C, n_head,
+                  scale, s)
+        dx = torch.empty_like(x)
+        dgamma = torch.zeros(C, dtype=f32, device=x.device)
+        dbeta = torch.zeros(C, dtype=f32, device=x.device)
+        _lib.call('og_rope_ln_bwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), eps, dq.data_ptr(), dk.data_ptr(),
+                  dv.data_ptr(), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, C, 1, S, s)
+        return dx, None, dgamma, dbeta, None, None, None
+
+
+class _TimeAttnFn(torch.autograd.Function):
+    """y = SDPA_causal(q, k, v; scale) + x over t for every pixel; q = LayerNorm(RoPE1d(x)); k = v = q, or the
+    projected latent-action conditioning (B, T, C) shared by all pixels (attention.py:347-371, 471)."""
+
+    @staticmethod
+    def forward(ctx, x, freq, gamma, beta, k_cond, v_cond, n_head: int, scale: float, eps: float):
+        _require_cuda(x, 'attention input')
+        x = _rows_bf16(x)
+        B, T, H, W, C = x.shape
+        P = H * W
+        s = _stream()
+        q = torch.empty_like(x)
+        _lib.call('og_rope_ln_fwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
+                  q.data_ptr(), B * T * P, C, P, T, s)
+        y = torch.empty_like(x)
+        bcast = k_cond is not None
+        if bcast:
+            kc = k_cond.detach().to(bf16).contiguous()
+            vc = v_cond.detach().to(bf16).contiguous()
+        else:
+            kc = vc = q
+        _lib.call('og_temporal_attn_fwd', q.data_ptr(), kc.data_ptr(), vc.data_ptr(), x.data_ptr(), y.data_ptr(), B, T,
+                  P, C, n_head, scale, int(bcast), s)
+        ctx.cfg = (n_head, scale, eps, bcast)
+        ctx.save_for_backward(x, q, kc if bcast else None, vc if bcast else None, freq, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, q, kc, vc, freq, gamma = ctx.saved_tensors
+        n_head, scale, eps, bcast = ctx.cfg
+        B, T, H, W, C = x.shape
+        P = H * W
+        s = _stream()
+        dy = _rows_bf16(dy)
+        dq = torch.empty_like(x)
+        dkc = dvc = None
+        if bcast:
+            dkc = torch.zeros((B, T, C), dtype=f32, device=x.device)
+            dvc = torch.zeros((B, T, C), dtype=f32, device=x.device)
+            _lib.call('og_temporal_attn_bwd', q.data_ptr(), kc.data_ptr(), vc.data_ptr(), dy.data_ptr(), dq.data_ptr(),
+                      None, None, dkc.data_ptr(), dvc.data_ptr(), B, T, P, C, n_head, scale, 1, s)
+            g1 = g2 = None
+        else:
+            dk, dv = torch.empty_like(x), torch.empty_like(x)
+            _lib.call('og_temporal_attn_bwd', q.data_ptr(), q.data_ptr(), q.data_ptr(), dy.data_ptr(), dq.data_ptr(),
+                      dk.data_ptr(), dv.data_ptr(), None, None, B, T, P, C, n_head, scale, 0, s)
+            g1, g2 = dk, dv
+        dx = torch.empty_like(x)
+        dgamma = torch.zeros(C, dtype=f32, device=x.device)
+        dbeta = torch.zeros(C, dtype=f32, device=x.device)
+        _lib.call('og_rope_ln_bwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), eps, dq.data_ptr(), _ptr(g1),
+                  _ptr(g2), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), B * T * P, C, P, T, s)
+        return dx, None, dgamma, dbeta, dkc, dvc, None, None, None
+
+
+class _FfnFn(torch.autograd.Function):
+    """y = Conv3d_k3(GroupNorm_G(x)) + x  — the ST block's "FFN" and its skip (attention.py:429-444, 472;
+    misc.py:92-98). The skip is added inside the conv epilogue, its gradient inside the GN backward pass."""
+
+    @staticmethod
+    def forward(ctx, x, gn_w, gn_b, conv_w, packed, geom: ConvGeom, G: int, eps: float):
+        _require_cuda(x, 'ffn input')
+        x = _rows_bf16(x)
+        B, T, H, W, C = x.shape
+        V = T * H * W
+        s = _stream()
+        dev = x.device
+        sums = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+        _lib.call('og_gn_stats', x.data_ptr(), B, V, C, G, sums.data_ptr(), s)
+        A = torch.empty((B, C), dtype=f32, device=dev)
+        Bc = torch.empty((B, C), dtype=f32, device=dev)
+        mr = torch.empty((B, G, 2), dtype=f32, device=dev)
+        _lib.call('og_gn_finalize', sums.data_ptr(), B, C, G, V, eps, gn_w.data_ptr(), gn_b.data_ptr(), None, None,
+                  A.data_ptr(), Bc.data_ptr(), mr.data_ptr(), s)
+        hn = torch.empty_like(x)
+        _lib.call('og_affine_act_fwd', x.data_ptr(), A.data_ptr(), Bc.data_ptr(), hn.data_ptr(), B, V, C, 0, s)
+        y = torch.empty_like(x)
+        ws = _workspace(dev, B * V * C * 4)
+        _conv_call('fwd', 2.0 * B * V * C * geom.k_main, 'og_conv3d_fwd', hn.data_ptr(), C, geom.kt, geom.kh, geom.kw,
+                   geom.pt, geom.ph, geom.pw, None, 0, packed.data_ptr(), packed.shape[1], None, None, x.data_ptr(),
+                   y.data_ptr(), 0, B, T, H, W, C, ws.data_ptr(), ws.numel(), s)
+        ctx.cfg = (geom, G)
+        ctx.save_for_backward(x, hn, A, Bc, mr, gn_w, gn_b, packed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, hn, A, Bc, mr, gn_w, gn_b, packed = ctx.saved_tensors
+        geom, G = ctx.cfg
+        B, T, H, W, C = x.shape
+        V = T * H * W
+        s = _stream()
+        dev = x.device
+        dy = _rows_bf16(dy)
+        ws = _workspace(dev, B * V * C * 4)
+        dh = torch.empty_like(x)
+        _conv_call('dgrad', 2.0 * B * V * C * geom.k_main, 'og_conv3d_dgrad', dy.data_ptr(), C, C, packed.data_ptr(),
+                   packed.shape[1], 0, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, dh.data_ptr(), 0, B, T, H,
+                   W, C, ws.data_ptr(), ws.numel(), s)
+        g = torch.zeros((C, geom.ntaps * C), dtype=f32, device=dev)
+        _conv_call('wgrad', 2.0 * B * V * C * geom.k_main, 'og_conv3d_wgrad', dy.data_ptr(), C, hn.data_ptr(), C,
+                   g.data_ptr(), g.shape[1], geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, B, T, H, W, s)
+        dw = g.view(C, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
+        S = torch.zeros((B, C, 2), dtype=f32, device=dev)
+        _lib.call('og_affine_act_bwd_reduce', dh.data_ptr(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), 0,
+                  S.data_ptr(), B, V, C, s)
+        Q = torch.empty((B, C), dtype=f32, device=dev)
+        R = torch.empty((B, C), dtype=f32, device=dev)
+        dgw = torch.zeros(C, dtype=f32, device=dev)
+        dgb = torch.zeros(C, dtype=f32, device=dev)
+        _lib.call('og_gn_bwd_finalize', S.data_ptr(), mr.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), None, B, C, G, V,
+                  Q.data_ptr(), R.data_ptr(), dgw.data_ptr(), dgb.data_ptr(), None, None, s)
+        dx = torch.empty_like(x)
+        _lib.call('og_affine_act_bwd_apply', dh.data_ptr(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), Q.data_ptr(),
+                  R.data_ptr(), dy.data_ptr(), dx.data_ptr(), 0, B, V, C, s)
+        return dx, dgw, dgb, dw, None, None, None, None
+
+
+def space_attention_res(x, freq, gamma, beta, n_head, scale, eps=1e-5):
+    return _SpaceAttnFn.apply(x, freq, gamma, beta, n_head, float(scale), float(eps))
+
+
+def time_attention_res(x, freq, gamma, beta, n_head, scale, k_cond=None, v_cond=None, eps=1e-5):
+    return _TimeAttnFn.apply(x, freq, gamma, beta, k_cond, v_cond, n_head, float(scale), float(eps))
+
+
+def ffn_res(x, gn_w, gn_b, conv_w, packed, geom, num_groups, eps=1e-5):
+    return _FfnFn.apply(x, gn_w, gn_b, conv_w, packed, geom, num_groups, float(eps))

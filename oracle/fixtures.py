@@ -33,25 +33,34 @@ MINI_D_CODEBOOK = 6
 MINI_VIDEO_SHAPE = (2, 3, 8, 32, 32)
 
 # LatentAction, pinned HEAD-valid form of genie/__init__.py:10-54, shrunk
+# d_head = 64 like the shipped blueprints (the tcgen05 attention kernel is specialised for it)
 MINI_ACT_ENC = (
-    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 32, 'transpose': True}),
-    ('spacetime_downsample', {'in_channels': 64, 'kernel_size': 3, 'time_factor': 1, 'space_factor': 2}),
-    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 32, 'transpose': True}),
+    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 64, 'transpose': True}),
+    ('spacetime_downsample', {'in_channels': 128, 'kernel_size': 3, 'time_factor': 1, 'space_factor': 2}),
+    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 64, 'transpose': True}),
 )
 MINI_ACT_DEC = (
-    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 32, 'transpose': True, 'has_ext': True,
+    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 64, 'transpose': True, 'has_ext': True,
                          'time_attn_kw': {'key_dim': 4}}),
-    ('depth2spacetime_upsample', {'in_channels': 64, 'kernel_size': 3, 'time_factor': 1, 'space_factor': 2}),
-    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 32, 'transpose': True, 'has_ext': True,
+    ('depth2spacetime_upsample', {'in_channels': 128, 'kernel_size': 3, 'time_factor': 1, 'space_factor': 2}),
+    ('space-time_attn', {'n_rep': 1, 'n_head': 2, 'd_head': 64, 'transpose': True, 'has_ext': True,
                          'time_attn_kw': {'key_dim': 4}}),
 )
 MINI_ACT_D_CODEBOOK = 4
-MINI_ACT_EMBD = 64
-MINI_ACT_VIDEO_SHAPE = (2, 3, 8, 16, 16)
+MINI_ACT_EMBD = 128
+MINI_ACT_VIDEO_SHAPE = (2, 3, 4, 16, 16)
 
-MINI_DYN_DESC = (('space-time_attn', {'n_rep': 2, 'n_head': 2, 'd_head': 32, 'transpose': False}),)
-MINI_DYN = dict(tok_vocab=64, act_vocab=16, embed_dim=64)
-MINI_DYN_TOKENS_SHAPE = (2, 8, 8, 8)
+MINI_DYN_DESC = (('space-time_attn', {'n_rep': 2, 'n_head': 2, 'd_head': 64, 'transpose': False}),)
+MINI_DYN = dict(tok_vocab=64, act_vocab=16, embed_dim=128)
+MINI_DYN_TOKENS_SHAPE = (2, 4, 8, 8)
+
+# SpaceTimeAttention block fixtures: (transpose, cond_dim, input shape)
+ST_BLOCK_CASES = (
+    (True, None, (2, 128, 2, 16, 16)),      # S = 256: two key tiles
+    (True, 4, (2, 128, 4, 8, 8)),           # S = 64: masked partial tile; temporal cond K/V
+    (False, None, (2, 4, 8, 8, 128)),       # channels-last logical layout (DynamicsModel)
+    (False, 4, (2, 4, 8, 8, 128)),
+)
 
 
 def bp(desc):

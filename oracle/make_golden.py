@@ -168,22 +168,21 @@ def gen_lfq():
 
 def gen_st_block():
     out = {}
-    for transpose in (True, False):
-        for cond_dim in (None, 4):
-            kw = {'time_attn_kw': {'key_dim': cond_dim}} if cond_dim else {}
-            m = SpaceTimeAttention(n_head=2, d_head=32, transpose=transpose, **kw)
-            sd = load_det(m)
-            shape = (2, 64, 4, 8, 8) if transpose else (2, 4, 8, 8, 64)
-            x = O.det_uniform(f'st.x.{transpose}', shape)
-            x.requires_grad_(True)
-            cond = O.det_uniform('st.cond', (2, 4, 4)).sign() if cond_dim else None
-            y = m(x, cond=(None, cond)) if cond_dim else m(x)
-            y.square().mean().backward()
-            oy = O.spacetime_attention(sd, '', x, 2, transpose, cond)
-            close(oy, y, f'SpaceTimeAttention transpose={transpose} cond={cond_dim}', rtol=2e-4, atol=2e-5)
-            out[f't{int(transpose)}_c{cond_dim or 0}'] = {
-                'y': y.detach(), 'dx': x.grad.clone(), 'grads': summarize_grads(grads_of(m))}
-            x.grad = None
+    for transpose, cond_dim, shape in fx.ST_BLOCK_CASES:
+        kw = {'time_attn_kw': {'key_dim': cond_dim}} if cond_dim else {}
+        m = SpaceTimeAttention(n_head=2, d_head=64, transpose=transpose, **kw)
+        sd = load_det(m)
+        tag = f't{int(transpose)}_c{cond_dim or 0}'
+        x = O.det_uniform(f'st.x.{tag}', shape)
+        x.requires_grad_(True)
+        t = shape[2] if transpose else shape[1]
+        cond = O.det_uniform('st.cond', (2, t, 4)).sign() if cond_dim else None
+        y = m(x, cond=(None, cond)) if cond_dim else m(x)
+        y.square().mean().backward()
+        oy = O.spacetime_attention(sd, '', x, 2, transpose, cond)
+        close(oy, y, f'SpaceTimeAttention {tag}', rtol=2e-4, atol=2e-5)
+        out[tag] = {'y': y.detach(), 'dx': x.grad.clone(), 'grads': summarize_grads(grads_of(m))}
+        x.grad = None
     torch.save(out, os.path.join(OUT, 'st_block.pt'))
 
 

@@ -175,7 +175,7 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
   CK(cudaMalloc(&out, V * c.cout * 4));
   CK(cudaMalloc(&ref, V * c.cout * 4));
   CK(cudaMemset(out, 0xFF, V * c.cout * 4));
-  int r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, x1, c.c1, w, ldw, b0, b1, out, 1, c.N, c.T, c.H,
+  int r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, x1, c.c1, w, ldw, b0, b1, nullptr, out, 1, c.N, c.T, c.H,
                         c.W, c.cout, g_ws, g_ws_bytes, 0);
   if (r != 0) {
     printf("  og_conv3d_fwd failed: %d %s\n", r, og_last_error());
@@ -199,7 +199,7 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
     __nv_bfloat16* ob;
     CK(cudaMalloc(&ob, (V * c.cout + 64) * 2));
     CK(cudaMemset(ob, 0x7F, (V * c.cout + 64) * 2));
-    r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, x1, c.c1, w, ldw, b0, b1, ob, 0, c.N, c.T, c.H,
+    r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, x1, c.c1, w, ldw, b0, b1, nullptr, ob, 0, c.N, c.T, c.H,
                       c.W, c.cout, g_ws, g_ws_bytes, 0);
     CK(cudaDeviceSynchronize());
     std::vector<__nv_bfloat16> hb(V * c.cout + 64);
@@ -341,7 +341,7 @@ static void bench_case(const Case& c, int iters) {
       if (i == 2) CK(cudaEventRecord(e0));
       int r = 0;
       if (which == 0)
-        r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, nullptr, 0, w, ldw, nullptr, nullptr, out, 0,
+        r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, nullptr, 0, w, ldw, nullptr, nullptr, nullptr, out, 0,
                           c.N, c.T, c.H, c.W, c.cout, g_ws, g_ws_bytes, 0);
       else if (which == 1)
         r = og_conv3d_dgrad(dy, c.cout, c.cout, w, ldw, 0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, dx, 0, c.N, c.T, c.H,
