@@ -229,6 +229,26 @@ int og_temporal_attn_bwd(const void* q, const void* k, const void* v, const void
                          int kv_bcast, og_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * DynamicsModel rows (genie/dynamics.py)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out[row] = bf16(tok_w[tok[row]] + act_w[act[row / rows_per_act]]): tok_emb(tokens) + act_emb(act_id) broadcast
+ * over (h, w) (dynamics.py:34-38, 55). tok: int64 [rows]; act: int64 [rows / rows_per_act]; weights fp32. */
+int og_embed_add_fwd(const int64_t* tok, const int64_t* act, const float* tok_w, const float* act_w, void* out,
+                     int64_t rows, int64_t rows_per_act, int C, int tok_vocab, int act_vocab, og_stream_t stream);
+/* d_tok_w / d_act_w (fp32, ACCUMULATED): scatter-add of dy (bf16 [rows][C]). */
+int og_embed_add_bwd(const int64_t* tok, const int64_t* act, const void* dy, float* d_tok_w, float* d_act_w,
+                     int64_t rows, int64_t rows_per_act, int C, int tok_vocab, int act_vocab, og_stream_t stream);
+
+/* cross_entropy(logits[mask], target[mask]) (dynamics.py:89-97). logits bf16 [rows][V]; mask uint8 [rows];
+ * row_lse fp32 [rows] (scratch, kept for backward); stats fp32 [2] zeroed by the caller: += (sum loss, count).
+ * Backward: dlogits = gloss / count * (softmax - onehot) on masked rows, 0 elsewhere (bf16 [rows][V]). */
+int og_masked_ce_fwd(const void* logits, const int64_t* target, const uint8_t* mask, int64_t rows, int V,
+                     float* row_lse, float* stats, og_stream_t stream);
+int og_masked_ce_bwd(const void* logits, const int64_t* target, const uint8_t* mask, const float* row_lse,
+                     const float* stats, const float* gloss, void* dlogits, int64_t rows, int V, og_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fused multi-tensor AdamW (genie/tokenizer.py:437-442) + bf16 operand refresh
  * ---------------------------------------------------------------------------------------------- */
 typedef struct og_adamw_tensor {

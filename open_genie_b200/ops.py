@@ -674,3 +674,80 @@ def time_attention_res(x, freq, gamma, beta, n_head, scale, k_cond=None, v_cond=
 
 def ffn_res(x, gn_w, gn_b, conv_w, packed, geom, num_groups, eps=1e-5):
     return _FfnFn.apply(x, gn_w, gn_b, conv_w, packed, geom, num_groups, float(eps))
+
+
+# ------------------------------------------------------------------------------------------------
+# row-wise linear layers on the conv GEMM kernel, embeddings, masked cross entropy
+# ------------------------------------------------------------------------------------------------
+def linear_rows(x2d: Tensor, weight: Tensor, bias: Optional[Tensor], packed: Tensor, out_f32: bool = False) -> Tensor:
+    """y[rows][N] = x[rows][K] @ weight[N][K]^T + bias  (nn.Linear) as a 1x1x1 conv over `rows` voxels.
+    weight: fp32 [N][K] (autograd leaf or view); packed: its bf16 copy [N][K]; K % 64 == 0."""
+    rows, K = x2d.shape
+    N = weight.shape[0]
+    geom = ConvGeom(K, N, (1, 1, 1))
+    x5 = x2d.reshape(1, 1, 1, rows, K).permute(0, 4, 1, 2, 3)
+    y5 = _Conv3dFn.apply(x5, weight.view(N, K, 1, 1, 1), bias, None, None, None, packed, geom, out_f32)
+    return y5.permute(0, 2, 3, 4, 1).reshape(rows, N)
+
+
+class _EmbedAddFn(torch.autograd.Function):
+    """tok_emb(tokens) + act_emb(act_id) broadcast over (h, w) -> (B,T,H,W,C) bf16 (dynamics.py:34-38, 55)."""
+
+    @staticmethod
+    def forward(ctx, tokens, act_id, tok_w, act_w):
+        _require_cuda(tok_w, 'embedding weight')
+        B, T, H, W = tokens.shape
+        C = tok_w.shape[1]
+        tok = tokens.detach().to(torch.int64).contiguous()
+        act = act_id.detach().to(torch.int64).contiguous()
+        out = torch.empty((B, T, H, W, C), dtype=bf16, device=tok_w.device)
+        _lib.call('og_embed_add_fwd', tok.data_ptr(), act.data_ptr(), tok_w.data_ptr(), act_w.data_ptr(), out.data_ptr(),
+                  B * T * H * W, H * W, C, tok_w.shape[0], act_w.shape[0], _stream())
+        ctx.save_for_backward(tok, act)
+        ctx.shapes = (tok_w.shape, act_w.shape, H * W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        tok, act = ctx.saved_tensors
+        ts, as_, hw = ctx.shapes
+        dy = _rows_bf16(dy)
+        dtw = torch.zeros(ts, dtype=f32, device=dy.device)
+        daw = torch.zeros(as_, dtype=f32, device=dy.device)
+        _lib.call('og_embed_add_bwd', tok.data_ptr(), act.data_ptr(), dy.data_ptr(), dtw.data_ptr(), daw.data_ptr(),
+                  tok.numel(), hw, ts[1], ts[0], as_[0], _stream())
+        return None, None, dtw, daw
+
+
+def embed_add(tokens, act_id, tok_w, act_w):
+    return _EmbedAddFn.apply(tokens, act_id, tok_w, act_w)
+
+
+class _MaskedCeFn(torch.autograd.Function):
+    """cross_entropy(logits[mask], target[mask]) with mean reduction (dynamics.py:89-97)."""
+
+    @staticmethod
+    def forward(ctx, logits2d, target, mask):
+        rows, V = logits2d.shape
+        lg = logits2d if (logits2d.dtype == bf16 and logits2d.is_contiguous()) else logits2d.to(bf16).contiguous()
+        tgt = target.detach().reshape(-1).to(torch.int64).contiguous()
+        msk = mask.detach().reshape(-1).to(torch.uint8).contiguous()
+        row_lse = torch.empty(rows, dtype=f32, device=lg.device)
+        stats = torch.zeros(2, dtype=f32, device=lg.device)
+        _lib.call('og_masked_ce_fwd', lg.data_ptr(), tgt.data_ptr(), msk.data_ptr(), rows, V, row_lse.data_ptr(),
+                  stats.data_ptr(), _stream())
+        ctx.save_for_backward(lg, tgt, msk, row_lse, stats)
+        return stats[0] / stats[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, tgt, msk, row_lse, stats = ctx.saved_tensors
+        gs = g.detach().to(f32).contiguous()
+        dl = torch.empty_like(lg)
+        _lib.call('og_masked_ce_bwd', lg.data_ptr(), tgt.data_ptr(), msk.data_ptr(), row_lse.data_ptr(), stats.data_ptr(),
+                  gs.data_ptr(), dl.data_ptr(), lg.shape[0], lg.shape[1], _stream())
+        return dl, None, None
+
+
+def masked_cross_entropy(logits2d, target, mask):
+    return _MaskedCeFn.apply(logits2d, target, mask)
