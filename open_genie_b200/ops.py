@@ -518,8 +518,8 @@ class _SpaceAttnFn(torch.autograd.Function):
                   q.data_ptr(), rows, C, 1, S, s)
         y, o = torch.empty_like(x), torch.empty_like(x)
         lse = torch.empty((B * T, n_head, S), dtype=f32, device=x.device)
-        _lib.call('og_flash_attn_fwd', q.data_ptr(), q.data_ptr(), q.data_ptr(), o.data_ptr(), x.data_ptr(),
-                  y.data_ptr(), lse.data_ptr(), B * T, S, C, n_head, scale, s)
+        _conv_call('attn_fwd', 4.0 * B * T * S * S * C, 'og_flash_attn_fwd', q.data_ptr(), q.data_ptr(), q.data_ptr(),
+                   o.data_ptr(), x.data_ptr(), y.data_ptr(), lse.data_ptr(), B * T, S, C, n_head, scale, s)
         ctx.cfg = (n_head, scale, eps)
         ctx.save_for_backward(x, q, o, lse, freq, gamma)
         return y
@@ -534,9 +534,9 @@ class _SpaceAttnFn(torch.autograd.Function):
         dy = _rows_bf16(dy)
         dq, dk, dv = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
         delta = torch.empty_like(lse)
-        _lib.call('og_flash_attn_bwd', q.data_ptr(), q.data_ptr(), q.data_ptr(), o.data_ptr(), dy.data_ptr(),
-                  lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B * T, S, C, n_head,
-                  scale, s)
+        _conv_call('attn_bwd', 10.0 * B * T * S * S * C, 'og_flash_attn_bwd', q.data_ptr(), q.data_ptr(), q.data_ptr(),
+                   o.data_ptr(), dy.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                   dv.data_ptr(), B * T, S, C, n_head, scale, s)
         dx = torch.empty_like(x)
         dgamma = torch.zeros(C, dtype=f32, device=x.device)
         dbeta = torch.zeros(C, dtype=f32, device=x.device)
