@@ -148,6 +148,13 @@ int og_im2col3d(const void* x, void* col, int N, int T, int H, int W, int C, int
 int og_col2im3d(const void* dcol, void* dx, int dx_f32, int N, int T, int H, int W, int C, int kt, int kh, int kw,
                 int st, int sh, int sw, int pt, int ph, int pw, int kpad, og_stream_t stream);
 
+/* BlurPooling3d with num_groups == 1 (genie/module/video.py:487-537): every output channel is
+ * blur_k(sum_c x[:, c]) with the normalised Pascal kernel, stride (st,sh,sw), padding (k-1)/2.
+ * backward == 0: x [N,T,H,W,cin] -> y [N,To,Ho,Wo,cout], scratch >= N*T*H*W floats.
+ * backward != 0: x = dy [N,To,Ho,Wo,cout] -> y = dx [N,T,H,W,cin], scratch >= N*To*Ho*Wo floats. */
+int og_blurpool3d(const void* x, void* y, float* scratch, int backward, int N, int T, int H, int W, int cin, int cout,
+                  int k, int st, int sh, int sw, og_stream_t stream);
+
 /* mse_loss (tokenizer.py:364, action.py:166): loss_sum += sum (rec - tgt)^2 ; rec NDHWC fp32, tgt NCDHW fp32.
  * Backward writes gscale * 2 (rec - tgt) / numel as bf16 NDHWC with cpad >= C channels (zero padded) so it
  * can feed og_conv3d_dgrad / og_conv3d_wgrad directly. gscale: device scalar or NULL (= 1). */

@@ -601,3 +601,141 @@ extern "C" int og_pad_channels(const void* x, int x_f32, void* y, int64_t rows, 
   g_launches.fetch_add(1);
   return OG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// BlurPooling3d (genie/module/video.py:487-537) with num_groups == 1: the reference repeats ONE Pascal kernel
+// over a dense (C_out x C_in) conv, so every output channel equals blur(sum_c x[:, c]).
+//   pass 1: s[v] = sum_c x[v][c]                       (fp32 [N*T*H*W])
+//   pass 2: y[vo][o] = sum_taps blur[tap] * s[vo*stride + tap - pad]   broadcast over o (bf16 NDHWC)
+// The adjoint (backward) is the same pair with the stencil transposed: g[vo] = sum_o dy[vo][o], then
+//   dx[v][c] = sum over (tap, vo) hitting v of blur[tap] * g[vo], broadcast over c.
+// ------------------------------------------------------------------------------------------------
+namespace og {
+
+__global__ void og_channel_sum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ s, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = w0; r < rows; r += nw) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += __bfloat162float(x[r * C + c]);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) s[r] = a;
+  }
+}
+
+__device__ __forceinline__ float pascal(int k, int i) {  // binomial(k-1, i)
+  float v = 1.f;
+  for (int j = 0; j < i; ++j) v = v * (float)(k - 1 - j) / (float)(j + 1);
+  return v;
+}
+
+// forward stencil + broadcast: one thread per (output voxel, 8-channel vector)
+__global__ void og_blur3d_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ y, int T, int H, int W,
+                                     int To, int Ho, int Wo, int k, int st, int sh, int sw, int Cout, float norm,
+                                     long long total_vec) {
+  const int cv = Cout >> 3;
+  const int pad = (k - 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long vo = i / cv;
+    const int wo = (int)(vo % Wo);
+    long long r = vo / Wo;
+    const int ho = (int)(r % Ho);
+    r /= Ho;
+    const int to = (int)(r % To);
+    const int n = (int)(r / To);
+    float acc = 0.f;
+    for (int it = 0; it < k; ++it) {
+      const int t = to * st + it - pad;
+      if (t < 0 || t >= T) continue;
+      for (int ih = 0; ih < k; ++ih) {
+        const int h = ho * sh + ih - pad;
+        if (h < 0 || h >= H) continue;
+        for (int iw = 0; iw < k; ++iw) {
+          const int w = wo * sw + iw - pad;
+          if (w < 0 || w >= W) continue;
+          acc += pascal(k, it) * pascal(k, ih) * pascal(k, iw) * s[(((long long)n * T + t) * H + h) * W + w];
+        }
+      }
+    }
+    acc *= norm;
+    const uint32_t p2 = pack_bf16x2(acc, acc);
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(p2, p2, p2, p2);
+  }
+}
+
+// adjoint stencil + broadcast: one thread per (input voxel, 8-channel vector)
+__global__ void og_blur3d_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ dx, int T, int H, int W,
+                                     int To, int Ho, int Wo, int k, int st, int sh, int sw, int Cin, float norm,
+                                     long long total_vec) {
+  const int cv = Cin >> 3;
+  const int pad = (k - 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long v = i / cv;
+    const int w = (int)(v % W);
+    long long r = v / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int t = (int)(r % T);
+    const int n = (int)(r / T);
+    float acc = 0.f;
+    for (int it = 0; it < k; ++it) {
+      const int tn = t + pad - it;
+      if (tn < 0 || tn % st || tn / st >= To) continue;
+      for (int ih = 0; ih < k; ++ih) {
+        const int hn = h + pad - ih;
+        if (hn < 0 || hn % sh || hn / sh >= Ho) continue;
+        for (int iw = 0; iw < k; ++iw) {
+          const int wn = w + pad - iw;
+          if (wn < 0 || wn % sw || wn / sw >= Wo) continue;
+          acc += pascal(k, it) * pascal(k, ih) * pascal(k, iw) *
+                 g[(((long long)n * To + tn / st) * Ho + hn / sh) * Wo + wn / sw];
+        }
+      }
+    }
+    acc *= norm;
+    const uint32_t p2 = pack_bf16x2(acc, acc);
+    reinterpret_cast<uint4*>(dx)[i] = make_uint4(p2, p2, p2, p2);
+  }
+}
+
+}  // namespace og
+
+extern "C" int og_blurpool3d(const void* x, void* y, float* scratch, int backward, int N, int T, int H, int W, int cin,
+                             int cout, int k, int st, int sh, int sw, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(x && y && scratch, "blurpool3d: null pointer");
+  OG_REQUIRE(cin % 8 == 0 && cout % 8 == 0 && k >= 1 && k <= 7 && (k & 1), "blurpool3d: need C %% 8 == 0 and odd k <= 7");
+  const int pad = (k - 1) / 2;
+  const int To = (T + 2 * pad - k) / st + 1, Ho = (H + 2 * pad - k) / sh + 1, Wo = (W + 2 * pad - k) / sw + 1;
+  float ksum = 0.f;
+  for (int i = 0; i < k; ++i) {
+    float v = 1.f;
+    for (int j = 0; j < i; ++j) v = v * (float)(k - 1 - j) / (float)(j + 1);
+    ksum += v;
+  }
+  const float norm = 1.f / (ksum * ksum * ksum);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!backward) {
+    // x: [N,T,H,W,cin] -> y: [N,To,Ho,Wo,cout]; scratch: N*T*H*W floats
+    const long long rows = (long long)N * T * H * W;
+    og_channel_sum_kernel<<<ew_blocks(rows, 8), 256, 0, s>>>((const __nv_bfloat16*)x, scratch, rows, cin);
+    OG_CHECK_CUDA(cudaGetLastError());
+    const long long total = (long long)N * To * Ho * Wo * (cout / 8);
+    og_blur3d_fwd_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(scratch, (__nv_bfloat16*)y, T, H, W, To, Ho, Wo, k, st, sh,
+                                                              sw, cout, norm, total);
+  } else {
+    // x: dy [N,To,Ho,Wo,cout] -> y: dx [N,T,H,W,cin]; scratch: N*To*Ho*Wo floats
+    const long long rows = (long long)N * To * Ho * Wo;
+    og_channel_sum_kernel<<<ew_blocks(rows, 8), 256, 0, s>>>((const __nv_bfloat16*)x, scratch, rows, cout);
+    OG_CHECK_CUDA(cudaGetLastError());
+    const long long total = (long long)N * T * H * W * (cin / 8);
+    og_blur3d_bwd_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(scratch, (__nv_bfloat16*)y, T, H, W, To, Ho, Wo, k, st, sh,
+                                                              sw, cin, norm, total);
+  }
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(2);
+  return OG_OK;
+}

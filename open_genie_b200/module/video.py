@@ -202,6 +202,32 @@ class DepthToSpaceTimeUpsample(Upsample):
         return self.out_channels
 
 
+class BlurPooling3d(nn.Module):
+    """Anti-aliased strided pooling — genie/module/video.py:487-537. With num_groups == 1 (the only value the
+    reference's VideoResidualBlock passes through its default) the repeated Pascal kernel makes every output
+    channel blur(sum_c x_c); that is what the kernel computes. Buffer 'blur' is kept for state_dict parity."""
+
+    def __init__(self, in_channels: int, kernel_size, out_channels: int | None = None, time_factor: int = 2,
+                 space_factor=2, num_groups: int = 1, **kwargs) -> None:
+        super().__init__()
+        kernel_size = _triple(kernel_size)
+        if len(set(kernel_size)) != 1 or num_groups != 1 or kwargs:
+            raise NotImplementedError('BlurPooling3d: cubic kernels and num_groups == 1 only')
+        if isinstance(space_factor, int):
+            space_factor = (space_factor, space_factor)
+        k = kernel_size[0]
+        row = torch.tensor([math.comb(k - 1, i) for i in range(k)], dtype=torch.float32)
+        ker = row[:, None, None] * row[None, :, None] * row[None, None, :]
+        self.register_buffer('blur', ker / ker.sum())
+        self.k = k
+        self.stride = (time_factor, *space_factor)
+        self.num_groups = num_groups
+        self.out_channels = out_channels
+
+    def forward(self, inp: Tensor) -> Tensor:
+        return ops.blurpool3d(inp, self.k, self.stride, default(self.out_channels, inp.shape[1]))
+
+
 class _GNParams(nn.GroupNorm):
     """nn.GroupNorm as parameter holder (keys 'weight', 'bias'); forward runs the fused kernel."""
     act = 'none'
@@ -227,9 +253,10 @@ class VideoResidualBlock(nn.Module):
                  pad_mode: str = 'constant', downsample=None, use_causal: bool = False, use_norm: bool = True,
                  use_blur: bool = True, act_fn: str = 'swish') -> None:
         super().__init__()
-        if exists(downsample):
-            raise NotImplementedError('VideoResidualBlock(downsample=...) (blur-pool variant) is not used by any '
-                                      'shipped blueprint and is outside the B200 hot-path scope')
+        if isinstance(downsample, int):
+            downsample = (downsample, downsample)
+        if exists(downsample) and not use_blur:
+            raise NotImplementedError('VideoResidualBlock(downsample=..., use_blur=False) is not used by any blueprint')
         if use_causal:
             raise NotImplementedError('VideoResidualBlock(use_causal=True) is not used by any shipped blueprint')
         if act_fn not in ('swish', 'silu') or not use_norm or pad_mode != 'constant':
@@ -237,11 +264,15 @@ class VideoResidualBlock(nn.Module):
         kernel_size = _triple(kernel_size)
         out_channels = default(out_channels, in_channels)
         conv = lambda ci, co, k: Conv3dParams(ci, co, k, causal=use_causal)
-        self.res = nn.Sequential(_Slot(), conv(in_channels, out_channels, 1))
+        tf, sf = downsample if exists(downsample) else (None, None)
+        down = (lambda c: BlurPooling3d(c, kernel_size, time_factor=tf, space_factor=sf, num_groups=num_groups)) \
+            if exists(downsample) else (lambda c: _Slot())
+        self.res = nn.Sequential(down(in_channels), conv(in_channels, out_channels, 1))
         self.main = nn.Sequential(
-            _GNParams(num_groups, in_channels), _Slot(), conv(in_channels, out_channels, kernel_size), _Slot(),
+            _GNParams(num_groups, in_channels), _Slot(), conv(in_channels, out_channels, kernel_size), down(out_channels),
             _GNParams(num_groups, out_channels), _Slot(), conv(out_channels, out_channels, kernel_size),
         )
+        self.has_down = exists(downsample)
         self.main[0].act = self.main[4].act = 'silu'
         self.main[6].fuse_shortcut(self.res[1])
         self.inp_channels, self.out_channels = in_channels, out_channels
@@ -250,8 +281,12 @@ class VideoResidualBlock(nn.Module):
     def forward(self, inp: Tensor) -> Tensor:
         h = self.main[0](inp)                # GN + SiLU (fused)
         h = self.main[2](h)                  # conv k3
+        skip = inp
+        if self.has_down:                    # anti-aliased down-sampling of both branches (video.py:589-621)
+            h = self.main[3](h)
+            skip = self.res[0](inp)
         h = self.main[4](h)                  # GN + SiLU (fused)
-        return self.main[6](h, x2=inp)       # conv k3 (+) 1x1x1 shortcut (+) add : one kernel
+        return self.main[6](h, x2=skip)      # conv k3 (+) 1x1x1 shortcut (+) add : one kernel
 
     @property
     def inp_dim(self):

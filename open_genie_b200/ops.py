@@ -412,6 +412,39 @@ def pixel_shuffle3d(x, p, q, r):
 
 
 # ------------------------------------------------------------------------------------------------
+# blur pooling (num_groups == 1)
+# ------------------------------------------------------------------------------------------------
+class _BlurPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k: int, stride, cout: int):
+        xi = to_internal(x, bf16)
+        B, C, T, H, W = xi.shape
+        st, sh, sw = stride
+        pad = (k - 1) // 2
+        To, Ho, Wo = (T + 2 * pad - k) // st + 1, (H + 2 * pad - k) // sh + 1, (W + 2 * pad - k) // sw + 1
+        y = empty_internal(B, cout, To, Ho, Wo, bf16, xi.device)
+        scratch = torch.empty(B * T * H * W, dtype=f32, device=xi.device)
+        _lib.call('og_blurpool3d', xi.data_ptr(), y.data_ptr(), scratch.data_ptr(), 0, B, T, H, W, C, cout, k, st, sh, sw,
+                  _stream())
+        ctx.cfg = (B, C, T, H, W, cout, k, st, sh, sw, To, Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, T, H, W, cout, k, st, sh, sw, To, Ho, Wo = ctx.cfg
+        dyb = _as_bf16_rows(dy, cout, cout)
+        dx = empty_internal(B, C, T, H, W, bf16, dy.device)
+        scratch = torch.empty(B * To * Ho * Wo, dtype=f32, device=dy.device)
+        _lib.call('og_blurpool3d', dyb.data_ptr(), dx.data_ptr(), scratch.data_ptr(), 1, B, T, H, W, C, cout, k, st, sh,
+                  sw, _stream())
+        return dx, None, None, None
+
+
+def blurpool3d(x, k, stride, cout):
+    return _BlurPoolFn.apply(x, k, tuple(stride), cout)
+
+
+# ------------------------------------------------------------------------------------------------
 # mse loss between an internal fp32 reconstruction and the reference-format target
 # ------------------------------------------------------------------------------------------------
 class _MseFn(torch.autograd.Function):

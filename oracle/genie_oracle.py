@@ -111,15 +111,18 @@ def blur_pool3d(x: Tensor, k: int, time_factor: int, space_factor: int, num_grou
     return F.conv3d(x, ker, stride=(time_factor, space_factor, space_factor), padding=pad, groups=num_groups)
 
 
-def video_residual_block(sd: StateDict, pre: str, x: Tensor, num_groups: int = 1) -> Tensor:
-    """VideoResidualBlock.forward as built by the MAGVIT2 blueprints (use_causal=False, no downsample)
-    — video.py:597-631 (layers) and 648 (main(x) + res(x)).
+def video_residual_block(sd: StateDict, pre: str, x: Tensor, num_groups: int = 1, downsample=None) -> Tensor:
+    """VideoResidualBlock.forward as built by the MAGVIT2 blueprints (use_causal=False) — video.py:597-631
+    (layers) and 648 (main(x) + res(x)); `downsample=(tf, sf)` adds the BlurPooling3d of both branches (589-621).
 
-    main = GN(num_groups) -> SiLU -> Conv3d(k3,p1) -> GN -> SiLU -> Conv3d(k3,p1); res = Conv3d(k1)."""
+    main = GN(num_groups) -> SiLU -> Conv3d(k3,p1) -> [blur] -> GN -> SiLU -> Conv3d(k3,p1); res = [blur] -> Conv3d(k1)."""
     h = F.group_norm(x, num_groups, sd[pre + 'main.0.weight'], sd[pre + 'main.0.bias'], 1e-5)
     h = F.silu(h)
     w = sd[pre + 'main.2.weight']
     h = F.conv3d(h, w, sd[pre + 'main.2.bias'], padding=tuple((k - 1) // 2 for k in w.shape[2:]))
+    if downsample is not None:
+        h = blur_pool3d(h, w.shape[2], downsample[0], downsample[1], num_groups)
+        x = blur_pool3d(x, w.shape[2], downsample[0], downsample[1], num_groups)
     h = F.group_norm(h, num_groups, sd[pre + 'main.4.weight'], sd[pre + 'main.4.bias'], 1e-5)
     h = F.silu(h)
     w = sd[pre + 'main.6.weight']

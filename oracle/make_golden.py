@@ -134,6 +134,13 @@ def gen_layers():
     out['video_residual'] = {'y': y.detach(), 'dx': x.grad.clone(), 'grads': summarize_grads(grads_of(m))}
     x.grad = None
 
+    m = VideoResidualBlock(64, 128, downsample=(2, 2))      # blur-pool variant (README / test blueprints)
+    sd = load_det(m)
+    y = m(x); y.square().mean().backward()
+    close(O.video_residual_block(sd, '', x, downsample=(2, 2)), y, 'VideoResidualBlock downsample')
+    out['video_residual_down'] = {'y': y.detach(), 'dx': x.grad.clone(), 'grads': summarize_grads(grads_of(m))}
+    x.grad = None
+
     m = DepthToSpaceTimeUpsample(64, kernel_size=3, time_factor=2, space_factor=2)
     sd = load_det(m)
     y = m(x); y.square().mean().backward()

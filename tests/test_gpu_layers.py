@@ -106,6 +106,35 @@ def test_video_residual_block(golden):
         assert abs(grads[k].norm().item() - n) / n < 5e-2, k
 
 
+def test_blur_pool_and_downsampling_residual_block(golden):
+    from open_genie_b200 import ops
+    from open_genie_b200.module.video import BlurPooling3d, VideoResidualBlock
+    k = golden('kats.pt')
+    xb = bf16_round(O.det_uniform('kat.blur.x', (1, 8, 4, 8, 8)))
+    bp = BlurPooling3d(8, 3).to(DEV)
+    assert torch.equal(bp.blur.cpu(), k['blur3'])
+    xg = xb.to(DEV).requires_grad_(True)
+    y = bp(xg)
+    xr = xb.clone().requires_grad_(True)
+    yo = O.blur_pool3d(xr, 3, 2, 2)
+    gy = bf16_round(O.det_uniform('blur.gy', tuple(yo.shape)))
+    y.backward(gy.to(DEV).to(y.dtype))
+    yo.backward(gy)
+    assert_close(ops.to_reference(y), bf16_round(yo), BF16_ULP, BF16_ULP * yo.abs().max().item(), 'blur fwd')
+    assert_close(xg.grad, xr.grad, 2 * BF16_ULP, 2 * BF16_ULP * xr.grad.abs().max().item(), 'blur bwd')
+    g = golden('layers.pt')['video_residual_down']
+    m = VideoResidualBlock(64, 128, downsample=(2, 2))
+    det_weights(m)
+    m.to(DEV)
+    assert {'res.0.blur', 'main.3.blur'} <= set(m.state_dict())
+    x = bf16_round(O.det_uniform('layers.x', (2, 64, 4, 8, 8)))
+    y, dx, grads = _run_layer(m, x)
+    assert y.shape == g['y'].shape == (2, 128, 2, 4, 4)
+    assert rel_l2(y, g['y']) < 2e-2 and rel_l2(dx, g['dx']) < 6e-2
+    for key, n in g['grads']['norm'].items():
+        assert abs(grads[key].norm().item() - n) / n < 6e-2, key
+
+
 def test_depth2spacetime_upsample(golden):
     from open_genie_b200.module.video import DepthToSpaceTimeUpsample
     g = golden('layers.pt')['depth2spacetime_upsample']

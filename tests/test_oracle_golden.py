@@ -60,6 +60,8 @@ def test_layer_vectors(golden):
     _close(O.spacetime_downsample(sd, '', x, 2, 2), g['spacetime_downsample']['y'])
     sd = _sd_for(VideoResidualBlock(64, 128))
     _close(O.video_residual_block(sd, '', x), g['video_residual']['y'])
+    sd = _sd_for(VideoResidualBlock(64, 128, downsample=(2, 2)))
+    _close(O.video_residual_block(sd, '', x, downsample=(2, 2)), g['video_residual_down']['y'])
     sd = _sd_for(DepthToSpaceTimeUpsample(64, kernel_size=3, time_factor=2, space_factor=2))
     _close(O.depth2spacetime_upsample(sd, '', x, 2, 2), g['depth2spacetime_upsample']['y'])
     sd = _sd_for(AdaptiveGroupNorm(6, 8, 64))
