@@ -63,21 +63,28 @@ uint64_t og_launch_count(void);
  * SpaceTimeAttention, attention.py:472).
  * Reads outside [0,T)x[0,H)x[0,W) are zero (pad_mode='constant').
  * workspace (optional, may be NULL): N*T*H*W*cout fp32 of scratch enables split-K for problems whose tiles
- * cannot fill the 148 SMs (small T*H*W, deep K); without it the same result is computed unsplit. */
+ * cannot fill the 148 SMs (small T*H*W, deep K); without it the same result is computed unsplit.
+ * gn_sums (optional): fp64 [N][2] += (sum, sum of squares) of the bf16 output per sample — the og_gn_stats
+ * result for a following GroupNorm(1, C) — produced in the GEMM epilogue when the tiling allows it, otherwise
+ * by an internal og_gn_stats pass; either way the caller just zeroes it first. */
 int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1, int c1,
                   const void* w, int ldw, const float* bias0, const float* bias1, const void* residual, void* out,
                   int out_f32, int N, int T, int H, int W, int cout, void* workspace, size_t workspace_bytes,
-                  og_stream_t stream);
+                  double* gn_sums, og_stream_t stream);
 
 /* Data gradient of the same convolution (autograd's conv3d backward-input, reached from
  * video.py:192 / 609-629 / 599-603 during loss.backward()).
  *   dx[n,t,h,w,ci] = sum_{it,ih,iw,co} dy[n, t-(it-pt), h-(ih-ph), w-(iw-pw), co] * w[co][k_off + tap*cin + ci]
  * dy: bf16 [N,T,H,W,cout] (cout % 64 == 0; a narrower gradient is zero-padded by the caller and
  * w_rows <= cout gives the number of real weight rows); w as above (k_off selects the segment inside
- * a packed row, k_off % 8 == 0); dx: [N,T,H,W,cin] (cin % 64 == 0), bf16 or fp32. */
+ * a packed row, k_off % 8 == 0); dx: [N,T,H,W,cin] (cin % 64 == 0), bf16 or fp32.
+ * red_* (optional): when dx is the gradient of y = act(x*A + B) (a GroupNorm+SiLU fed by this conv's input),
+ * red_S[n][c] += (sum_v dpre, sum_v dpre*x) with dpre = dx * act'(x*A+B) — exactly og_affine_act_bwd_reduce on
+ * (dx, red_x) — is accumulated in the GEMM epilogue (or by an internal pass when the tiling does not allow it). */
 int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int k_off, int kt, int kh, int kw,
                     int pt, int ph, int pw, void* dx, int dx_f32, int N, int T, int H, int W, int cin,
-                    void* workspace, size_t workspace_bytes, og_stream_t stream);
+                    void* workspace, size_t workspace_bytes, const void* red_x, const float* red_A,
+                    const float* red_B, int red_act, float* red_S, og_stream_t stream);
 
 /* Weight gradient (autograd's conv3d backward-weight). ACCUMULATES into dw (caller zeroes it):
  *   dw[co][tap][ci] += sum_{n,t,h,w} dy[n,t,h,w,co] * x[n, t+it-pt, h+ih-ph, w+iw-pw, ci]

@@ -55,6 +55,13 @@ struct IgemmParams {
   int m_sub;   // M sub-tiles (of 128 rows) per CTA tile sharing one B stage: 1 or 2
   int fast_store;  // bf16 output, n_out % 64 == 0, block_n % 64 == 0: coalesced staged stores
   const __nv_bfloat16* residual;  // optional bf16 [voxels][n_out] added to the output (out = conv + bias + residual)
+  // fused epilogue reductions (fast_store path, one sample per CTA tile):
+  double* gn_sums;             // forward: [N][2] += (sum y, sum y^2) of the bf16-rounded output (GroupNorm(1,C) statistics)
+  const __nv_bfloat16* red_x;  // data gradient: GN input x [voxels][n_out] ...
+  const float* red_A;          // ... per-(sample, channel) scale / shift of y = act(x*A+B) ...
+  const float* red_B;
+  float* red_S;                // ... S[n][c] += (sum dpre, sum dpre*x), dpre = d * act'(x*A+B)   (og_affine_act_bwd_reduce)
+  int red_act;
   int splits;      // split-K factor (1 = none): each work item covers a k-block range and reduces into `ws`
   float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zeroed by the launcher) when splits > 1
 };
@@ -104,6 +111,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   float* bias_s = reinterpret_cast<float*>(bars + 32);                    // [256] bias0+bias1 of the current N tile
   uint8_t* stage_s = reinterpret_cast<uint8_t*>(bars + 32) + 1024;        // 4 warps x 32 rows x 128 B store staging
+  float* coef_s = reinterpret_cast<float*>(stage_s + 4 * 4096);          // [2][256] A, B of the current sample / N tile
+  float* red_s = coef_s + 512;                                            // [256][2] column sums of the current tile
+  double* stat_s = reinterpret_cast<double*>(red_s + 512);                // [2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -248,6 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float fl_s = 0.f, fl_ss = 0.f;
+    for (int j = threadIdx.x - 64; j < 512; j += 128) red_s[j] = 0.f;
+    if (threadIdx.x == 64) stat_s[0] = stat_s[1] = 0.0;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
       const int tile = item / p.splits;
       const int m_super = tile / p.num_n_tiles;
@@ -306,9 +320,14 @@ __global__ void __launch_bounds__(kThreads, 1)
               if (p.bias1) b += __ldg(p.bias1 + col);
             }
             bias_s[j] = b;
+            if (p.red_S) {
+              coef_s[j] = col < p.n_out ? __ldg(p.red_A + (long long)tc.n0 * p.n_out + col) : 0.f;
+              coef_s[256 + j] = col < p.n_out ? __ldg(p.red_B + (long long)tc.n0 * p.n_out + col) : 0.f;
+            }
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        float st_s = 0.f, st_ss = 0.f;
         uint8_t* my_stage = stage_s + (warp - 2) * 4096;
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
         for (int c = 0; c < p.block_n; c += 64) {
@@ -332,22 +351,90 @@ __global__ void __launch_bounds__(kThreads, 1)
               }
             }
           }
+          // fold the bias in: from here on v0 / v1 are the final fp32 outputs of this row
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v0[j] = __float_as_uint(__uint_as_float(v0[j]) + bias_s[c + j]);
+            v1[j] = __float_as_uint(__uint_as_float(v1[j]) + bias_s[c + 32 + j]);
+          }
+          if (p.gn_sums || p.red_S) {
+            if (p.gn_sums && row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float r0 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v0[j])));
+                const float r1 = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v1[j])));
+                st_s += r0 + r1;
+                st_ss = fmaf(r0, r0, fmaf(r1, r1, st_ss));
+              }
+            }
+            if (p.red_S) {
+              float d1[64], d2[64];
+              const uint4* xp = reinterpret_cast<const uint4*>(p.red_x + vox * p.ldo + col0 + c);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (row_ok) u = __ldg(xp + j);
+                const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 xf = __bfloat1622float2(hh[e]);
+#pragma unroll
+                  for (int q2 = 0; q2 < 2; ++q2) {
+                    const int idx = 8 * j + 2 * e + q2;
+                    const float xv = q2 ? xf.y : xf.x;
+                    const uint32_t raw = idx < 32 ? v0[idx] : v1[idx - 32];
+                    float dv = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw)));  // what bwd_apply will read
+                    if (p.red_act) {
+                      const float pre = fmaf(xv, coef_s[c + idx], coef_s[256 + c + idx]);
+                      const float sg = 1.f / (1.f + __expf(-pre));
+                      dv *= sg * (1.f + pre * (1.f - sg));
+                    }
+                    if (!row_ok) dv = 0.f;
+                    d1[idx] = dv;
+                    d2[idx] = dv * xv;
+                  }
+                }
+              }
+              // warp transpose-reduce: afterwards lane l holds the 32-row sums of columns l and l+32
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                  float* arr = (w == 0 ? d1 : d2) + half * 32;
+#pragma unroll
+                  for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int j = 0; j < off; ++j) {
+                      const float send = up ? arr[j] : arr[j + off];
+                      const float keep = up ? arr[j + off] : arr[j];
+                      arr[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                  }
+                }
+              }
+              atomicAdd(&red_s[2 * (c + lane)], d1[0]);
+              atomicAdd(&red_s[2 * (c + lane) + 1], d2[0]);
+              atomicAdd(&red_s[2 * (c + 32 + lane)], d1[32]);
+              atomicAdd(&red_s[2 * (c + 32 + lane) + 1], d2[32]);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]) + bias_s[c + 8 * j + 0], __uint_as_float(v0[8 * j + 1]) + bias_s[c + 8 * j + 1]);
-            u.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]) + bias_s[c + 8 * j + 2], __uint_as_float(v0[8 * j + 3]) + bias_s[c + 8 * j + 3]);
-            u.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]) + bias_s[c + 8 * j + 4], __uint_as_float(v0[8 * j + 5]) + bias_s[c + 8 * j + 5]);
-            u.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]) + bias_s[c + 8 * j + 6], __uint_as_float(v0[8 * j + 7]) + bias_s[c + 8 * j + 7]);
+            u.x = pack_bf16x2(__uint_as_float(v0[8 * j + 0]), __uint_as_float(v0[8 * j + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7]));
             *reinterpret_cast<uint4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = u;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]) + bias_s[c + 32 + 8 * j + 0], __uint_as_float(v1[8 * j + 1]) + bias_s[c + 32 + 8 * j + 1]);
-            u.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]) + bias_s[c + 32 + 8 * j + 2], __uint_as_float(v1[8 * j + 3]) + bias_s[c + 32 + 8 * j + 3]);
-            u.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]) + bias_s[c + 32 + 8 * j + 4], __uint_as_float(v1[8 * j + 5]) + bias_s[c + 32 + 8 * j + 5]);
-            u.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]) + bias_s[c + 32 + 8 * j + 6], __uint_as_float(v1[8 * j + 7]) + bias_s[c + 32 + 8 * j + 7]);
+            u.x = pack_bf16x2(__uint_as_float(v1[8 * j + 0]), __uint_as_float(v1[8 * j + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7]));
             *reinterpret_cast<uint4*>(my_stage + lane * 128 + (((j + 4) ^ (lane & 7)) << 4)) = u;
           }
           __syncwarp();
@@ -362,6 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           __syncwarp();
         }
+        fl_s += st_s;
+        fl_ss += st_ss;
         continue;
       }
 
@@ -424,6 +513,37 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (p.fast_store && p.splits == 1 && (p.gn_sums || p.red_S)) {
+        // flush this tile's fused reductions (all rows of a CTA tile belong to one sample: host-checked)
+        const TileCoord tcf = decode_m_tile(p, m_super * p.m_sub);
+        if (p.gn_sums) {
+          for (int o = 16; o > 0; o >>= 1) {
+            fl_s += __shfl_xor_sync(0xffffffffu, fl_s, o);
+            fl_ss += __shfl_xor_sync(0xffffffffu, fl_ss, o);
+          }
+          if (lane == 0) {
+            atomicAdd(&stat_s[0], (double)fl_s);
+            atomicAdd(&stat_s[1], (double)fl_ss);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = threadIdx.x - 64;
+        if (p.red_S) {
+          const int col0f = n_tile * p.block_n;
+          for (int j = et; j < 2 * p.block_n; j += 128) {
+            const int col = col0f + (j >> 1);
+            if (col < p.n_out) atomicAdd(&p.red_S[((long long)tcf.n0 * p.n_out + col) * 2 + (j & 1)], red_s[j]);
+            red_s[j] = 0.f;
+          }
+        }
+        if (p.gn_sums && et == 0) {
+          atomicAdd(&p.gn_sums[(long long)tcf.n0 * 2], stat_s[0]);
+          atomicAdd(&p.gn_sums[(long long)tcf.n0 * 2 + 1], stat_s[1]);
+          stat_s[0] = 0.0;
+          stat_s[1] = 0.0;
+        }
+        fl_s = fl_ss = 0.f;
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -472,7 +592,8 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
                         const void* w, int ldw, int k_off, int b_mn_major, int b_rows /*K rows for MN-major*/,
                         int b_ntaps, const float* bias0, const float* bias1, const void* residual, void* out,
                         int out_f32, int N, int T, int H, int W, int n_out, void* workspace, size_t workspace_bytes,
-                        cudaStream_t stream) {
+                        double* gn_sums, const void* red_x, const float* red_A, const float* red_B, int red_act,
+                        float* red_S, cudaStream_t stream) {
   OG_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0 && n_out > 0, "conv3d: empty problem");
   int bw, bh, bt, bn;
   choose_voxel_box(kBlockM, N, T, H, W, &bw, &bh, &bt, &bn);
@@ -538,7 +659,7 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
       }
     }
   }
-  const int tail_bytes = 256 /*barriers*/ + 1024 /*bias*/ + 4 * 4096 /*store staging*/;
+  const int tail_bytes = 256 /*barriers*/ + 1024 /*bias*/ + 4 * 4096 /*store staging*/ + 4352 /*fused reductions*/;
   int stages = (227 * 1024 - 1024 /*align slack*/ - tail_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
@@ -584,6 +705,15 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  // fused epilogue reductions need: staged bf16 stores, no split-K, every CTA tile inside one sample
+  const int tiles_per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
+  const bool can_fuse = p.fast_store && p.splits == 1 && bn == 1 && (tiles_per_sample % p.m_sub == 0) && n_out <= 65536;
+  p.gn_sums = (gn_sums && can_fuse) ? gn_sums : nullptr;
+  p.red_S = (red_S && can_fuse) ? red_S : nullptr;
+  p.red_x = reinterpret_cast<const __nv_bfloat16*>(red_x);
+  p.red_A = red_A;
+  p.red_B = red_B;
+  p.red_act = red_act;
   const int total_tiles = ((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles * p.splits;
   int grid = num_sms();
   if (grid > total_tiles) grid = total_tiles;
@@ -598,6 +728,18 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
     OG_CHECK_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
   }
+  // requested reductions that could not be fused: run the stand-alone passes on the stored output
+  if (gn_sums && !p.gn_sums) {
+    OG_REQUIRE(!out_f32, "conv3d: GroupNorm statistics need a bf16 output");
+    int r = og_gn_stats(out, N, (int64_t)T * H * W, n_out, 1, gn_sums, (og_stream_t)stream);
+    if (r != OG_OK) return r;
+  }
+  if (red_S && !p.red_S) {
+    OG_REQUIRE(!out_f32, "conv3d: fused backward reduction needs a bf16 output");
+    int r = og_affine_act_bwd_reduce(out, red_x, red_A, red_B, red_act, red_S, N, (int64_t)T * H * W, n_out,
+                                     (og_stream_t)stream);
+    if (r != OG_OK) return r;
+  }
   return OG_OK;
 }
 
@@ -606,7 +748,7 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
 extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1,
                              int c1, const void* w, int ldw, const float* bias0, const float* bias1,
                              const void* residual, void* out, int out_f32, int N, int T, int H, int W, int cout,
-                             void* workspace, size_t workspace_bytes, og_stream_t stream) {
+                             void* workspace, size_t workspace_bytes, double* gn_sums, og_stream_t stream) {
   using namespace og;
   OG_REQUIRE(x0 && w && out, "conv3d_fwd: null pointer");
   OG_REQUIRE(c0 > 0 && c0 % 64 == 0, "conv3d_fwd: c0=%d must be a positive multiple of 64 (use the im2col path)", c0);
@@ -619,12 +761,15 @@ extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int
   segs[0] = IgemmSeg{c0 / 64, kt, kh, kw, pt, ph, pw};
   segs[1] = IgemmSeg{c1 / 64, 1, 1, 1, 0, 0, 0};
   return launch_igemm(x0, c0, x1, c1, segs, x1 ? 2 : 1, +1, w, ldw, 0, 0, 0, 0, bias0, bias1, residual, out, out_f32, N, T,
-                      H, W, cout, workspace, workspace_bytes, (cudaStream_t)stream);
+                      H, W, cout, workspace, workspace_bytes, gn_sums, nullptr, nullptr, nullptr, 0, nullptr,
+                      (cudaStream_t)stream);
 }
 
 extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int k_off, int kt, int kh,
                                int kw, int pt, int ph, int pw, void* dx, int dx_f32, int N, int T, int H, int W,
-                               int cin, void* workspace, size_t workspace_bytes, og_stream_t stream) {
+                               int cin, void* workspace, size_t workspace_bytes, const void* red_x,
+                               const float* red_A, const float* red_B, int red_act, float* red_S,
+                               og_stream_t stream) {
   using namespace og;
   OG_REQUIRE(dy && w && dx, "conv3d_dgrad: null pointer");
   OG_REQUIRE(cout > 0 && cout % 64 == 0, "conv3d_dgrad: cout=%d must be a multiple of 64", cout);
@@ -634,5 +779,6 @@ extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void*
   IgemmSeg segs[1];
   segs[0] = IgemmSeg{cout / 64, kt, kh, kw, pt, ph, pw};
   return launch_igemm(dy, cout, nullptr, 0, segs, 1, -1, w, ldw, k_off, 1, w_rows, kt * kh * kw, nullptr, nullptr, nullptr, dx,
-                      dx_f32, N, T, H, W, cin, workspace, workspace_bytes, (cudaStream_t)stream);
+                      dx_f32, N, T, H, W, cin, workspace, workspace_bytes, nullptr, red_x, red_A, red_B, red_act, red_S,
+                      (cudaStream_t)stream);
 }

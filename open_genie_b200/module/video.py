@@ -279,6 +279,18 @@ class VideoResidualBlock(nn.Module):
         self.in_channels = in_channels
 
     def forward(self, inp: Tensor) -> Tensor:
+        if not self.has_down and inp.is_cuda:
+            # whole block as one autograd node: GroupNorm statistics / backward reductions come out of the GEMM
+            # epilogues, the shortcut gradient is added inside the last apply pass. The statistics of the output
+            # ride along on the tensor so that the next block's first GroupNorm needs no pass of its own.
+            g1, c1, g2, c2, cr = self.main[0], self.main[2], self.main[4], self.main[6], self.res[1]
+            ops._require_cuda(c1.weight, 'module parameters')
+            sums = getattr(inp, '_og_gn_sums', None) if g1.num_groups == 1 else None
+            y, y_sums = ops.residual_block(inp, sums, g1.weight, g1.bias, c1.weight, c1.bias, g2.weight, g2.bias,
+                                           c2.weight, c2.bias, cr.weight, cr.bias, c1.packed(), c2.packed(), c1.geom,
+                                           c2.geom, g1.num_groups, g1.eps)
+            y._og_gn_sums = y_sums
+            return y
         h = self.main[0](inp)                # GN + SiLU (fused)
         h = self.main[2](h)                  # conv k3
         skip = inp

@@ -204,7 +204,7 @@ class _Conv3dFn(torch.autograd.Function):
             _conv_call('fwd', 2.0 * B * T * H * W * geom.cout * (geom.k_main + c1),
                        'og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
                       _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), None, y.data_ptr(), int(out_f32),
-                      B, T, H, W, geom.cout, ws.data_ptr(), ws.numel(), s)
+                      B, T, H, W, geom.cout, ws.data_ptr(), ws.numel(), None, s)
         else:
             assert x2 is None
             col = torch.empty((B * To * Ho * Wo, geom.kpad), dtype=bf16, device=x.device)
@@ -213,7 +213,7 @@ class _Conv3dFn(torch.autograd.Function):
             _conv_call('fwd', 2.0 * B * To * Ho * Wo * geom.cout * geom.k_main,
                        'og_conv3d_fwd', col.data_ptr(), geom.kpad, 1, 1, 1, 0, 0, 0, None, 0, packed.data_ptr(), ldw,
                       _ptr(bias), None, None, y.data_ptr(), int(out_f32), 1, 1, 1, B * To * Ho * Wo, geom.cout,
-                      ws.data_ptr(), ws.numel(), s)
+                      ws.data_ptr(), ws.numel(), None, s)
         ctx.geom = geom
         ctx.in_shape = (B, C, T, H, W)
         ctx.has_bias = (bias is not None, bias2 is not None)
@@ -251,7 +251,8 @@ class _Conv3dFn(torch.autograd.Function):
                 dx = empty_internal(B, C, T, H, W, bf16, dev)
                 _conv_call('dgrad', 2.0 * B * T * H * W * cout * geom.k_main,
                            'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, geom.kt, geom.kh,
-                           geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, ws.data_ptr(), ws.numel(), s)
+                           geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, ws.data_ptr(), ws.numel(),
+                           None, None, None, 0, None, s)
             if need[1]:
                 g = wgrad(xs, C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, ctx.w_shapes[0], (B, T, H, W))
                 dw = g.view(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
@@ -261,7 +262,8 @@ class _Conv3dFn(torch.autograd.Function):
                     dx2 = empty_internal(B, c1, T, H, W, bf16, dev)
                     _conv_call('dgrad', 2.0 * B * T * H * W * cout * c1,
                                'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, geom.k_main,
-                               1, 1, 1, 0, 0, 0, dx2.data_ptr(), 0, B, T, H, W, c1, ws.data_ptr(), ws.numel(), s)
+                               1, 1, 1, 0, 0, 0, dx2.data_ptr(), 0, B, T, H, W, c1, ws.data_ptr(), ws.numel(),
+                               None, None, None, 0, None, s)
                 if need[4]:
                     g = wgrad(x2i, c1, 1, 1, 1, 0, 0, 0, ctx.w_shapes[1], (B, T, H, W))
                     dw2 = g.view(cout, 1, 1, 1, c1).permute(0, 4, 1, 2, 3)
@@ -271,7 +273,7 @@ class _Conv3dFn(torch.autograd.Function):
                 dcol = torch.empty_like(col)
                 _conv_call('dgrad', 2.0 * B * To * Ho * Wo * cout * geom.k_main,
                            'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, 1, 1, 1, 0, 0, 0,
-                           dcol.data_ptr(), 0, 1, 1, 1, B * To * Ho * Wo, geom.kpad, None, 0, s)
+                           dcol.data_ptr(), 0, 1, 1, 1, B * To * Ho * Wo, geom.kpad, None, 0, None, None, None, 0, None, s)
                 dx = empty_internal(B, C, T, H, W, bf16, dev)
                 _lib.call('og_col2im3d', dcol.data_ptr(), dx.data_ptr(), 0, B, T, H, W, C, geom.kt, geom.kh, geom.kw,
                           geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, geom.kpad, s)
@@ -659,7 +661,7 @@ class _FfnFn(torch.autograd.Function):
         ws = _workspace(dev, B * V * C * 4)
         _conv_call('fwd', 2.0 * B * V * C * geom.k_main, 'og_conv3d_fwd', hn.data_ptr(), C, geom.kt, geom.kh, geom.kw,
                    geom.pt, geom.ph, geom.pw, None, 0, packed.data_ptr(), packed.shape[1], None, None, x.data_ptr(),
-                   y.data_ptr(), 0, B, T, H, W, C, ws.data_ptr(), ws.numel(), s)
+                   y.data_ptr(), 0, B, T, H, W, C, ws.data_ptr(), ws.numel(), None, s)
         ctx.cfg = (geom, G)
         ctx.save_for_backward(x, hn, A, Bc, mr, gn_w, gn_b, packed)
         return y
@@ -675,16 +677,15 @@ class _FfnFn(torch.autograd.Function):
         dy = _rows_bf16(dy)
         ws = _workspace(dev, B * V * C * 4)
         dh = torch.empty_like(x)
+        S = torch.zeros((B, C, 2), dtype=f32, device=dev)
+        # data gradient with the GroupNorm backward reduction fused into its epilogue
         _conv_call('dgrad', 2.0 * B * V * C * geom.k_main, 'og_conv3d_dgrad', dy.data_ptr(), C, C, packed.data_ptr(),
                    packed.shape[1], 0, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, dh.data_ptr(), 0, B, T, H,
-                   W, C, ws.data_ptr(), ws.numel(), s)
+                   W, C, ws.data_ptr(), ws.numel(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), 0, S.data_ptr(), s)
         g = torch.zeros((C, geom.ntaps * C), dtype=f32, device=dev)
         _conv_call('wgrad', 2.0 * B * V * C * geom.k_main, 'og_conv3d_wgrad', dy.data_ptr(), C, hn.data_ptr(), C,
                    g.data_ptr(), g.shape[1], geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, B, T, H, W, s)
         dw = g.view(C, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
-        S = torch.zeros((B, C, 2), dtype=f32, device=dev)
-        _lib.call('og_affine_act_bwd_reduce', dh.data_ptr(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), 0,
-                  S.data_ptr(), B, V, C, s)
         Q = torch.empty((B, C), dtype=f32, device=dev)
         R = torch.empty((B, C), dtype=f32, device=dev)
         dgw = torch.zeros(C, dtype=f32, device=dev)
@@ -784,3 +785,129 @@ class _MaskedCeFn(torch.autograd.Function):
 
 def masked_cross_entropy(logits2d, target, mask):
     return _MaskedCeFn.apply(logits2d, target, mask)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused VideoResidualBlock (no down-sampling): GN+SiLU -> conv -> GN+SiLU -> conv (+) 1x1x1 shortcut (+) add
+# ------------------------------------------------------------------------------------------------
+class _ResBlockFn(torch.autograd.Function):
+    """One autograd node for the whole block (genie/module/video.py:539-656) so that
+      * GroupNorm statistics of each conv output come out of the producing GEMM's epilogue (gn_sums),
+      * the GroupNorm backward reductions come out of the data-gradient GEMM's epilogue (red_S),
+      * the shortcut's data gradient is added inside the last backward apply pass (no stand-alone add),
+    leaving per block: 2 apply passes forward, 2 apply passes backward, 2 column-sum passes, and the GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, x_sums, g1w, g1b, w1, b1, g2w, g2b, w2, b2, wres, bres, packed1, packed2, geom1: ConvGeom,
+                geom2: ConvGeom, G: int, eps: float):
+        _require_cuda(x, 'residual block input')
+        xi = to_internal(x, bf16)
+        B, C0, T, H, W = xi.shape
+        C1 = geom1.cout
+        V = T * H * W
+        s = _stream()
+        dev = xi.device
+        if x_sums is None:
+            x_sums = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+            _lib.call('og_gn_stats', xi.data_ptr(), B, V, C0, G, x_sums.data_ptr(), s)
+        coef = torch.empty((2, 2, B, max(C0, C1)), dtype=f32, device=dev)       # A1,B1 / A2,B2
+        mr = torch.empty((2, B, G, 2), dtype=f32, device=dev)
+        A1, B1, A2, B2 = coef[0, 0, :, :C0], coef[0, 1, :, :C0], coef[1, 0, :, :C1], coef[1, 1, :, :C1]
+        A1, B1 = torch.empty((B, C0), dtype=f32, device=dev), torch.empty((B, C0), dtype=f32, device=dev)
+        A2, B2 = torch.empty((B, C1), dtype=f32, device=dev), torch.empty((B, C1), dtype=f32, device=dev)
+        _lib.call('og_gn_finalize', x_sums.data_ptr(), B, C0, G, V, eps, g1w.data_ptr(), g1b.data_ptr(), None, None,
+                  A1.data_ptr(), B1.data_ptr(), mr[0].data_ptr(), s)
+        a1 = empty_internal(B, C0, T, H, W, bf16, dev)
+        _lib.call('og_affine_act_fwd', xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), a1.data_ptr(), B, V, C0, 1, s)
+        ws = _workspace(dev, B * V * C1 * 4)
+        fuse_stats = G == 1
+        sums2 = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+        h1 = empty_internal(B, C1, T, H, W, bf16, dev)
+        _conv_call('fwd', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_fwd', a1.data_ptr(), C0, geom1.kt, geom1.kh,
+                   geom1.kw, geom1.pt, geom1.ph, geom1.pw, None, 0, packed1.data_ptr(), packed1.shape[1], _ptr(b1), None,
+                   None, h1.data_ptr(), 0, B, T, H, W, C1, ws.data_ptr(), ws.numel(),
+                   sums2.data_ptr() if fuse_stats else None, s)
+        if not fuse_stats:
+            _lib.call('og_gn_stats', h1.data_ptr(), B, V, C1, G, sums2.data_ptr(), s)
+        _lib.call('og_gn_finalize', sums2.data_ptr(), B, C1, G, V, eps, g2w.data_ptr(), g2b.data_ptr(), None, None,
+                  A2.data_ptr(), B2.data_ptr(), mr[1].data_ptr(), s)
+        a2 = empty_internal(B, C1, T, H, W, bf16, dev)
+        _lib.call('og_affine_act_fwd', h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), a2.data_ptr(), B, V, C1, 1, s)
+        y = empty_internal(B, C1, T, H, W, bf16, dev)
+        y_sums = torch.zeros((B, 1, 2), dtype=torch.float64, device=dev)
+        _conv_call('fwd', 2.0 * B * V * C1 * (geom2.k_main + C0), 'og_conv3d_fwd', a2.data_ptr(), C1, geom2.kt, geom2.kh,
+                   geom2.kw, geom2.pt, geom2.ph, geom2.pw, xi.data_ptr(), C0, packed2.data_ptr(), packed2.shape[1],
+                   _ptr(b2), _ptr(bres), None, y.data_ptr(), 0, B, T, H, W, C1, ws.data_ptr(), ws.numel(),
+                   y_sums.data_ptr(), s)
+        ctx.cfg = (geom1, geom2, G, b1 is not None, b2 is not None, bres is not None)
+        ctx.save_for_backward(xi, a1, h1, a2, A1, B1, A2, B2, mr, g1w, g1b, g2w, g2b, packed1, packed2)
+        ctx.mark_non_differentiable(y_sums)
+        return y, y_sums
+
+    @staticmethod
+    def backward(ctx, dy, _dsums):
+        xi, a1, h1, a2, A1, B1, A2, B2, mr, g1w, g1b, g2w, g2b, packed1, packed2 = ctx.saved_tensors
+        geom1, geom2, G, has_b1, has_b2, has_bres = ctx.cfg
+        B, C0, T, H, W = xi.shape
+        C1 = geom1.cout
+        V = T * H * W
+        s = _stream()
+        dev = xi.device
+        dyb = _as_bf16_rows(dy, C1, C1)
+        ws = _workspace(dev, B * V * max(C0, C1) * 4)
+        ld2 = packed2.shape[1]
+
+        def wgrad(dyt, cout, xin, cin, g):
+            gr = torch.zeros((cout, g.ntaps * cin), dtype=f32, device=dev)
+            _conv_call('wgrad', 2.0 * B * V * cout * cin * g.ntaps, 'og_conv3d_wgrad', dyt.data_ptr(), cout,
+                       xin.data_ptr(), cin, gr.data_ptr(), gr.shape[1], g.kt, g.kh, g.kw, g.pt, g.ph, g.pw, B, T, H, W, s)
+            return gr.view(cout, g.kt, g.kh, g.kw, cin).permute(0, 4, 1, 2, 3)
+
+        gone = ConvGeom(C0, C1, (1, 1, 1))
+        db2 = torch.zeros(C1, dtype=f32, device=dev)
+        _lib.call('og_colsum', dyb.data_ptr(), B * V, C1, C1, db2.data_ptr(), s)
+        dw2 = wgrad(dyb, C1, a2, C1, geom2)
+        dwres = wgrad(dyb, C1, xi, C0, gone)
+        # conv2 data gradient + fused GN2 backward reduction
+        S2 = torch.zeros((B, C1, 2), dtype=f32, device=dev)
+        d_a2 = empty_internal(B, C1, T, H, W, bf16, dev)
+        _conv_call('dgrad', 2.0 * B * V * C1 * geom2.k_main, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(),
+                   ld2, 0, geom2.kt, geom2.kh, geom2.kw, geom2.pt, geom2.ph, geom2.pw, d_a2.data_ptr(), 0, B, T, H, W, C1,
+                   ws.data_ptr(), ws.numel(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1, S2.data_ptr(), s)
+        Q2, R2 = torch.empty((B, C1), dtype=f32, device=dev), torch.empty((B, C1), dtype=f32, device=dev)
+        dg2w, dg2b = torch.zeros(C1, dtype=f32, device=dev), torch.zeros(C1, dtype=f32, device=dev)
+        _lib.call('og_gn_bwd_finalize', S2.data_ptr(), mr[1].data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, B, C1, G, V,
+                  Q2.data_ptr(), R2.data_ptr(), dg2w.data_ptr(), dg2b.data_ptr(), None, None, s)
+        d_h1 = empty_internal(B, C1, T, H, W, bf16, dev)
+        _lib.call('og_affine_act_bwd_apply', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), Q2.data_ptr(),
+                  R2.data_ptr(), None, d_h1.data_ptr(), 1, B, V, C1, s)
+        db1 = torch.zeros(C1, dtype=f32, device=dev)
+        _lib.call('og_colsum', d_h1.data_ptr(), B * V, C1, C1, db1.data_ptr(), s)
+        dw1 = wgrad(d_h1, C1, a1, C0, geom1)
+        dx = None
+        dg1w, dg1b = torch.zeros(C0, dtype=f32, device=dev), torch.zeros(C0, dtype=f32, device=dev)
+        # conv1 data gradient + fused GN1 backward reduction; shortcut data gradient; GN1 backward apply adds both
+        S1 = torch.zeros((B, C0, 2), dtype=f32, device=dev)
+        d_a1 = empty_internal(B, C0, T, H, W, bf16, dev)
+        _conv_call('dgrad', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_dgrad', d_h1.data_ptr(), C1, C1,
+                   packed1.data_ptr(), packed1.shape[1], 0, geom1.kt, geom1.kh, geom1.kw, geom1.pt, geom1.ph, geom1.pw,
+                   d_a1.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(), xi.data_ptr(), A1.data_ptr(),
+                   B1.data_ptr(), 1, S1.data_ptr(), s)
+        dx_res = empty_internal(B, C0, T, H, W, bf16, dev)
+        _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
+                   geom2.k_main, 1, 1, 1, 0, 0, 0, dx_res.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
+                   None, None, None, 0, None, s)
+        Q1, R1 = torch.empty((B, C0), dtype=f32, device=dev), torch.empty((B, C0), dtype=f32, device=dev)
+        _lib.call('og_gn_bwd_finalize', S1.data_ptr(), mr[0].data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, B, C0, G, V,
+                  Q1.data_ptr(), R1.data_ptr(), dg1w.data_ptr(), dg1b.data_ptr(), None, None, s)
+        if ctx.needs_input_grad[0]:
+            dx = empty_internal(B, C0, T, H, W, bf16, dev)
+            _lib.call('og_affine_act_bwd_apply', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(),
+                      Q1.data_ptr(), R1.data_ptr(), dx_res.data_ptr(), dx.data_ptr(), 1, B, V, C0, s)
+        return (dx, None, dg1w, dg1b, dw1, db1 if has_b1 else None, dg2w, dg2b, dw2, db2 if has_b2 else None, dwres,
+                (db2.clone() if has_b2 else db2) if has_bres else None, None, None, None, None, None, None)
+
+
+def residual_block(x, x_sums, g1w, g1b, w1, b1, g2w, g2b, w2, b2, wres, bres, packed1, packed2, geom1, geom2, G, eps):
+    return _ResBlockFn.apply(x, x_sums, g1w, g1b, w1, b1, g2w, g2b, w2, b2, wres, bres, packed1, packed2, geom1, geom2, G,
+                             float(eps))

@@ -176,7 +176,7 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
   CK(cudaMalloc(&ref, V * c.cout * 4));
   CK(cudaMemset(out, 0xFF, V * c.cout * 4));
   int r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, x1, c.c1, w, ldw, b0, b1, nullptr, out, 1, c.N, c.T, c.H,
-                        c.W, c.cout, g_ws, g_ws_bytes, 0);
+                        c.W, c.cout, g_ws, g_ws_bytes, nullptr, 0);
   if (r != 0) {
     printf("  og_conv3d_fwd failed: %d %s\n", r, og_last_error());
     return false;
@@ -200,7 +200,7 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
     CK(cudaMalloc(&ob, (V * c.cout + 64) * 2));
     CK(cudaMemset(ob, 0x7F, (V * c.cout + 64) * 2));
     r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, x1, c.c1, w, ldw, b0, b1, nullptr, ob, 0, c.N, c.T, c.H,
-                      c.W, c.cout, g_ws, g_ws_bytes, 0);
+                      c.W, c.cout, g_ws, g_ws_bytes, nullptr, 0);
     CK(cudaDeviceSynchronize());
     std::vector<__nv_bfloat16> hb(V * c.cout + 64);
     std::vector<float> hr(V * c.cout);
@@ -225,7 +225,7 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
     CK(cudaMalloc(&dxr, V * c.c0 * 4));
     CK(cudaMemset(dx, 0xFF, V * c.c0 * 4));
     r = og_conv3d_dgrad(dy, c.cout, c.cout, w, ldw, 0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, dx, 1, c.N, c.T, c.H, c.W,
-                        c.c0, g_ws, g_ws_bytes, 0);
+                        c.c0, g_ws, g_ws_bytes, nullptr, nullptr, nullptr, 0, nullptr, 0);
     if (r != 0) {
       printf("  og_conv3d_dgrad failed: %d %s\n", r, og_last_error());
       ok = false;
@@ -245,7 +245,7 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
       CK(cudaMalloc(&dxb, (V * c.c0 + 64) * 2));
       CK(cudaMemset(dxb, 0x7F, (V * c.c0 + 64) * 2));  // canary after the tensor
       r = og_conv3d_dgrad(dy, c.cout, c.cout, w, ldw, 0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, dxb, 0, c.N, c.T, c.H, c.W,
-                          c.c0, g_ws, g_ws_bytes, 0);
+                          c.c0, g_ws, g_ws_bytes, nullptr, nullptr, nullptr, 0, nullptr, 0);
       CK(cudaDeviceSynchronize());
       std::vector<__nv_bfloat16> hb(V * c.c0 + 64);
       std::vector<float> hr(V * c.c0);
@@ -264,7 +264,7 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
       float *dx1, *dx1r;
       CK(cudaMalloc(&dx1, V * c.c1 * 4));
       CK(cudaMalloc(&dx1r, V * c.c1 * 4));
-      r = og_conv3d_dgrad(dy, c.cout, c.cout, w, ldw, ntaps * c.c0, 1, 1, 1, 0, 0, 0, dx1, 1, c.N, c.T, c.H, c.W, c.c1, g_ws, g_ws_bytes, 0);
+      r = og_conv3d_dgrad(dy, c.cout, c.cout, w, ldw, ntaps * c.c0, 1, 1, 1, 0, 0, 0, dx1, 1, c.N, c.T, c.H, c.W, c.c1, g_ws, g_ws_bytes, nullptr, nullptr, nullptr, 0, nullptr, 0);
       if (r != 0) {
         printf("  og_conv3d_dgrad(shortcut) failed: %d %s\n", r, og_last_error());
         ok = false;
@@ -342,10 +342,10 @@ static void bench_case(const Case& c, int iters) {
       int r = 0;
       if (which == 0)
         r = og_conv3d_fwd(x0, c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, nullptr, 0, w, ldw, nullptr, nullptr, nullptr, out, 0,
-                          c.N, c.T, c.H, c.W, c.cout, g_ws, g_ws_bytes, 0);
+                          c.N, c.T, c.H, c.W, c.cout, g_ws, g_ws_bytes, nullptr, 0);
       else if (which == 1)
         r = og_conv3d_dgrad(dy, c.cout, c.cout, w, ldw, 0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, dx, 0, c.N, c.T, c.H,
-                            c.W, c.c0, g_ws, g_ws_bytes, 0);
+                            c.W, c.c0, g_ws, g_ws_bytes, nullptr, nullptr, nullptr, 0, nullptr, 0);
       else
         r = og_conv3d_wgrad(dy, c.cout, x0, c.c0, dw, (int64_t)ntaps * c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, c.N,
                             c.T, c.H, c.W, 0);

@@ -26,12 +26,12 @@ def test_argument_validation_returns_status_codes_not_crashes():
     lib = _lib.load()
     # null pointers / bad channel counts are rejected before any CUDA call
     rc = lib.og_conv3d_fwd(None, 64, 3, 3, 3, 1, 1, 1, None, 0, None, 1728, None, None, None, None, 0, 1, 2, 8, 8, 64,
-                           None, 0, None)
+                           None, 0, None, None)
     assert rc == -1 and b'null pointer' in lib.og_last_error()
     buf = ctypes.create_string_buffer(64)
     p = ctypes.addressof(buf)
     rc = lib.og_conv3d_fwd(p, 48, 3, 3, 3, 1, 1, 1, None, 0, p, 1296, None, None, None, p, 0, 1, 2, 8, 8, 64, None, 0,
-                           None)
+                           None, None)
     assert rc == -1 and b'multiple of 64' in lib.og_last_error()
     rc = lib.og_conv3d_wgrad(p, 64, p, 72, p, 72, 1, 1, 1, 0, 0, 0, 1, 1, 8, 8, None)
     assert rc == -1
