@@ -24,6 +24,10 @@ def _stream() -> int:
 
 
 _WS = {}
+# tuning switches (environment): fuse GroupNorm statistics / backward reductions into the GEMM epilogues
+import os as _os
+FUSE_STATS = _os.environ.get('OG_FUSE_STATS', '1') != '0'
+FUSE_RED = _os.environ.get('OG_FUSE_RED', '0') != '0'   # measured: costs more in the dgrad epilogue than the pass it saves
 
 
 def _workspace(dev, nbytes: int):
@@ -820,7 +824,7 @@ class _ResBlockFn(torch.autograd.Function):
         a1 = empty_internal(B, C0, T, H, W, bf16, dev)
         _lib.call('og_affine_act_fwd', xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), a1.data_ptr(), B, V, C0, 1, s)
         ws = _workspace(dev, B * V * C1 * 4)
-        fuse_stats = G == 1
+        fuse_stats = G == 1 and FUSE_STATS
         sums2 = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
         h1 = empty_internal(B, C1, T, H, W, bf16, dev)
         _conv_call('fwd', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_fwd', a1.data_ptr(), C0, geom1.kt, geom1.kh,
@@ -838,7 +842,9 @@ class _ResBlockFn(torch.autograd.Function):
         _conv_call('fwd', 2.0 * B * V * C1 * (geom2.k_main + C0), 'og_conv3d_fwd', a2.data_ptr(), C1, geom2.kt, geom2.kh,
                    geom2.kw, geom2.pt, geom2.ph, geom2.pw, xi.data_ptr(), C0, packed2.data_ptr(), packed2.shape[1],
                    _ptr(b2), _ptr(bres), None, y.data_ptr(), 0, B, T, H, W, C1, ws.data_ptr(), ws.numel(),
-                   y_sums.data_ptr(), s)
+                   y_sums.data_ptr() if FUSE_STATS else None, s)
+        if not FUSE_STATS:
+            _lib.call('og_gn_stats', y.data_ptr(), B, V, C1, 1, y_sums.data_ptr(), s)
         ctx.cfg = (geom1, geom2, G, b1 is not None, b2 is not None, bres is not None)
         ctx.save_for_backward(xi, a1, h1, a2, A1, B1, A2, B2, mr, g1w, g1b, g2w, g2b, packed1, packed2)
         ctx.mark_non_differentiable(y_sums)
@@ -873,7 +879,11 @@ class _ResBlockFn(torch.autograd.Function):
         d_a2 = empty_internal(B, C1, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * geom2.k_main, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(),
                    ld2, 0, geom2.kt, geom2.kh, geom2.kw, geom2.pt, geom2.ph, geom2.pw, d_a2.data_ptr(), 0, B, T, H, W, C1,
-                   ws.data_ptr(), ws.numel(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1, S2.data_ptr(), s)
+                   ws.data_ptr(), ws.numel(), *((h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1, S2.data_ptr())
+                                                if FUSE_RED else (None, None, None, 0, None)), s)
+        if not FUSE_RED:
+            _lib.call('og_affine_act_bwd_reduce', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1,
+                      S2.data_ptr(), B, V, C1, s)
         Q2, R2 = torch.empty((B, C1), dtype=f32, device=dev), torch.empty((B, C1), dtype=f32, device=dev)
         dg2w, dg2b = torch.zeros(C1, dtype=f32, device=dev), torch.zeros(C1, dtype=f32, device=dev)
         _lib.call('og_gn_bwd_finalize', S2.data_ptr(), mr[1].data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, B, C1, G, V,
@@ -891,8 +901,12 @@ class _ResBlockFn(torch.autograd.Function):
         d_a1 = empty_internal(B, C0, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_dgrad', d_h1.data_ptr(), C1, C1,
                    packed1.data_ptr(), packed1.shape[1], 0, geom1.kt, geom1.kh, geom1.kw, geom1.pt, geom1.ph, geom1.pw,
-                   d_a1.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(), xi.data_ptr(), A1.data_ptr(),
-                   B1.data_ptr(), 1, S1.data_ptr(), s)
+                   d_a1.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
+                   *((xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), 1, S1.data_ptr()) if FUSE_RED
+                     else (None, None, None, 0, None)), s)
+        if not FUSE_RED:
+            _lib.call('og_affine_act_bwd_reduce', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), 1,
+                      S1.data_ptr(), B, V, C0, s)
         dx_res = empty_internal(B, C0, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
                    geom2.k_main, 1, 1, 1, 0, 0, 0, dx_res.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
