@@ -131,6 +131,20 @@ int og_affine_act_bwd_apply(const void* dy, const void* x, const float* A, const
                             const float* R, const void* add, void* dx, int act, int N, int64_t V, int C,
                             og_stream_t stream);
 
+/* One-launch forms of the two pairs above, used on the training hot path (same math, same outputs):
+ * og_gn_act_fwd  = og_gn_finalize + og_affine_act_fwd  (A, B, mean_rstd are still written for backward);
+ * og_gn_act_bwd  = og_gn_bwd_finalize + og_affine_act_bwd_apply, S/mean_rstd NULL => pure activation backward.
+ * dx_colsum (optional, float[C], ACCUMULATED) receives sum over rows of dx — the bias gradient of the
+ * convolution that produced x (nn.Conv3d bias of ResidualBlock conv #1, genie/module/video.py:609-615).
+ * Both need (C/G) % 8 == 0. */
+int og_gn_act_fwd(const void* x, const double* sums, const float* gamma, const float* beta, const float* cond_scale,
+                  const float* cond_shift, float eps, int G, int act, void* y, float* A, float* B, float* mean_rstd,
+                  int N, int64_t V, int C, og_stream_t stream);
+int og_gn_act_bwd(const void* dy, const void* x, const float* A, const float* B, const float* S,
+                  const float* mean_rstd, const float* gamma, const float* beta, const float* cond_scale, int G, int act,
+                  const void* add, void* dx, float* dgamma, float* dbeta, float* dcond_scale, float* dcond_shift,
+                  float* dx_colsum, int N, int64_t V, int C, og_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * layout / data movement
  * ---------------------------------------------------------------------------------------------- */

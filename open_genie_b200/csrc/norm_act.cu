@@ -18,10 +18,18 @@
 namespace og {
 extern std::atomic<uint64_t> g_launches;
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// sigmoid through the hardware tanh (one MUFU op instead of ex2 + an IEEE divide): these passes run at
+// ~1.6 T elements/s when HBM-bound, which leaves ~20 issue slots per element — the exp/divide form alone used half.
+// |error| <= 2^-11 on sigmoid, far inside the bf16 rounding of every tensor these kernels write.
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(t, 0.5f, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float silu_grad_f(float x) {
-  const float s = 1.f / (1.f + __expf(-x));
-  return s * (1.f + x * (1.f - s));
+  const float s = sigmoid_f(x);
+  return s * fmaf(x, 1.f - s, 1.f);
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -299,11 +307,227 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// (blocks_per_sample, N) grid of ~4 blocks per SM; every block owns a contiguous range of whole
+
+// ------------------------------------------------------------------------------------------------
+// fused finalize + apply (forward): grid (blocks_per_sample, N), block 256, thread -> (channel vector, row lane).
+// Every thread derives the scale/shift of its own 8 channels from the fp64 group sums (a handful of flops),
+// so the stand-alone finalize launch and the per-element coefficient loads disappear; block 0 of each
+// sample stores A, B and (mean, rstd) for the backward pass.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4)
+    og_gn_act_fwd_kernel(const uint4* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const float* __restrict__ cond_scale,
+                         const float* __restrict__ cond_shift, float* __restrict__ A, float* __restrict__ B,
+                         float* __restrict__ mean_rstd, uint4* __restrict__ y, long long V, int C, int G,
+                         double inv_count, float eps, int act, long long rows_per_block) {
+  const int cvs = C >> 3;
+  const int n = blockIdx.y;
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = (r_begin + rows_per_block < V) ? r_begin + rows_per_block : V;
+  const int lanes = 256 / cvs;
+  const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
+  if (rl >= lanes || r_begin >= V) return;
+  float av[8], bv[8];
+  const long long o = (long long)n * C + cv * 8;
+  {
+    const int cpg = C / G;
+    const int g = (cv * 8) / cpg;
+    const double s = sums[((long long)n * G + g) * 2], ss = sums[((long long)n * G + g) * 2 + 1];
+    const double mean = s * inv_count;
+    double var = ss * inv_count - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float mu = (float)mean;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float ga = gamma ? gamma[cv * 8 + k] : 1.f, be = beta ? beta[cv * 8 + k] : 0.f;
+      float a = rstd * ga, b = be - mu * rstd * ga;
+      if (cond_scale) {
+        const float sc = cond_scale[o + k];
+        a *= sc;
+        b *= sc;
+      }
+      if (cond_shift) b += cond_shift[o + k];
+      av[k] = a;
+      bv[k] = b;
+    }
+    if (blockIdx.x == 0 && rl == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        A[o + k] = av[k];
+        B[o + k] = bv[k];
+      }
+      if ((cv * 8) % cpg == 0) {
+        mean_rstd[((long long)n * G + g) * 2] = mu;
+        mean_rstd[((long long)n * G + g) * 2 + 1] = rstd;
+      }
+    }
+  }
+  const long long base = (long long)n * V * cvs + cv;
+  long long r = r_begin + rl;
+  for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = __ldg(x + base + (r + (long long)j * lanes) * cvs);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack8(u[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float pre = fmaf(f[k], av[k], bv[k]);
+        f[k] = act ? silu_f(pre) : pre;
+      }
+      y[base + (r + (long long)j * lanes) * cvs] = pack8(f);
+    }
+  }
+  for (; r < r_end; r += lanes) {
+    float f[8];
+    unpack8(__ldg(x + base + r * cvs), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float pre = fmaf(f[k], av[k], bv[k]);
+      f[k] = act ? silu_f(pre) : pre;
+    }
+    y[base + r * cvs] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused finalize + apply (backward): every block re-derives the per-group means m1, m2 of its sample from
+// S (2*C floats, L2-resident), each thread the P/Q/R of its 8 channels; block 0 of the sample also emits
+// dgamma / dbeta / dcond. Optionally accumulates the per-channel column sum of dx (the bias gradient of
+// the convolution that produced x).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3)
+    og_gn_act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ A,
+                         const float* __restrict__ B, const float* __restrict__ S, const float* __restrict__ mean_rstd,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const float* __restrict__ cond_scale, const uint4* __restrict__ add, uint4* __restrict__ dx,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcond_scale,
+                         float* __restrict__ dcond_shift, float* __restrict__ dx_colsum, long long V, int C, int G,
+                         double inv_M, int act, long long rows_per_block) {
+  const int cvs = C >> 3;
+  const int n = blockIdx.y;
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  const long long r_end = (r_begin + rows_per_block < V) ? r_begin + rows_per_block : V;
+  const int lanes = 256 / cvs;
+  const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
+  const int cpg = C / G;
+  __shared__ double m1s[64], m2s[64];
+  extern __shared__ float cs_s[];  // [C] column sums of dx (only when dx_colsum)
+  for (int i = threadIdx.x; i < G; i += 256) m1s[i] = m2s[i] = 0.0;
+  if (dx_colsum)
+    for (int i = threadIdx.x; i < C; i += 256) cs_s[i] = 0.f;
+  __syncthreads();
+  if (S) {
+    const bool warp_uniform = (cpg % 32) == 0;  // then C % 32 == 0 and a warp's 32 channels share one group
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const int g = c / cpg;
+      const float mu = mean_rstd[((long long)n * G + g) * 2], rstd = mean_rstd[((long long)n * G + g) * 2 + 1];
+      const float s1 = S[((long long)n * C + c) * 2], s2 = S[((long long)n * C + c) * 2 + 1];
+      const float t1 = s1, t2 = rstd * (s2 - mu * s1);
+      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      const float sc = cond_scale ? cond_scale[(long long)n * C + c] : 1.f;
+      const float gp = ga * sc;
+      double v1 = (double)(gp * t1), v2 = (double)(gp * t2);
+      if (warp_uniform) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+          atomicAdd(&m1s[g], v1);
+          atomicAdd(&m2s[g], v2);
+        }
+      } else {
+        atomicAdd(&m1s[g], v1);
+        atomicAdd(&m2s[g], v2);
+      }
+      if (blockIdx.x == 0) {
+        if (dgamma) atomicAdd(&dgamma[c], sc * t2);
+        if (dbeta) atomicAdd(&dbeta[c], sc * t1);
+        if (dcond_scale) dcond_scale[(long long)n * C + c] = ga * t2 + be * t1;
+        if (dcond_shift) dcond_shift[(long long)n * C + c] = t1;
+      }
+    }
+  }
+  __syncthreads();
+  const bool active = rl < lanes && r_begin < V;
+  if (active) {
+    float av[8], bv[8], qv[8], rv[8], cs[8];
+    const long long o = (long long)n * C + cv * 8;
+    {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(A + o)), a1 = __ldg(reinterpret_cast<const float4*>(A + o) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(B + o)), b1 = __ldg(reinterpret_cast<const float4*>(B + o) + 1);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+    }
+    float q = 0.f, rr = 0.f;
+    if (S) {
+      const int g = (cv * 8) / cpg;
+      const float mu = mean_rstd[((long long)n * G + g) * 2], rstd = mean_rstd[((long long)n * G + g) * 2 + 1];
+      const float m1 = (float)(m1s[g] * inv_M), m2 = (float)(m2s[g] * inv_M);
+      q = -rstd * rstd * m2;
+      rr = rstd * (m2 * rstd * mu - m1);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      qv[k] = q;
+      rv[k] = rr;
+      cs[k] = 0.f;
+    }
+    const long long base = (long long)n * V * cvs + cv;
+    auto body = [&](const uint4& ux, const uint4& ud, const uint4& ua, long long idx) {
+      float fx[8], fd[8], fa[8], out[8];
+      unpack8(ux, fx);
+      unpack8(ud, fd);
+      if (add) unpack8(ua, fa);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
+        float v = fmaf(av[k], dpre, fmaf(qv[k], fx[k], rv[k]));
+        if (add) v += fa[k];
+        out[k] = v;
+        cs[k] += v;
+      }
+      dx[idx] = pack8(out);
+    };
+    long long r = r_begin + rl;
+    for (; r + (long long)lanes < r_end; r += 2LL * lanes) {
+      const long long i0 = base + r * cvs, i1 = base + (r + lanes) * cvs;
+      const uint4 x0 = __ldg(x + i0), d0 = __ldg(dy + i0), x1 = __ldg(x + i1), d1 = __ldg(dy + i1);
+      uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+      if (add) {
+        a0 = __ldg(add + i0);
+        a1 = __ldg(add + i1);
+      }
+      body(x0, d0, a0, i0);
+      body(x1, d1, a1, i1);
+    }
+    for (; r < r_end; r += lanes) {
+      const long long i0 = base + r * cvs;
+      uint4 a0 = make_uint4(0, 0, 0, 0);
+      if (add) a0 = __ldg(add + i0);
+      body(__ldg(x + i0), __ldg(dy + i0), a0, i0);
+    }
+    if (dx_colsum) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&cs_s[cv * 8 + k], cs[k]);
+    }
+  }
+  if (dx_colsum) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&dx_colsum[i], cs_s[i]);
+  }
+}
+
+// (blocks_per_sample, N) grid of ~per_sm blocks per SM; every block owns a contiguous range of whole
 // kStatRows-row groups of one sample.
-static dim3 reduce_grid(int N, long long V, long long* rows_per_block) {
+static dim3 reduce_grid(int N, long long V, long long* rows_per_block, int per_sm = 4) {
   long long groups = (V + kStatRows - 1) / kStatRows;
-  long long want = (4LL * num_sms() + N - 1) / N;
+  long long want = ((long long)per_sm * num_sms() + N - 1) / N;
   if (want < 1) want = 1;
   if (want > groups) want = groups;
   const long long gpb = (groups + want - 1) / want;
@@ -398,6 +622,44 @@ extern "C" int og_affine_act_bwd_apply(const void* dy, const void* x, const floa
   og_affine_act_bwd_apply_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, Q, R,
       reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), V, C, total, act);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_gn_act_fwd(const void* x, const double* sums, const float* gamma, const float* beta,
+                             const float* cond_scale, const float* cond_shift, float eps, int G, int act, void* y,
+                             float* A, float* B, float* mean_rstd, int N, int64_t V, int C, og_stream_t stream) {
+  OG_REQUIRE(x && sums && y && A && B && mean_rstd, "gn_act_fwd: null pointer");
+  OG_REQUIRE(C % 8 == 0 && C <= 2048 && G >= 1 && G <= 64 && C % G == 0 && (C / G) % 8 == 0,
+             "gn_act_fwd: need C%%8==0, C<=2048, G<=64, (C/G)%%8==0 (C=%d G=%d)", C, G);
+  long long rpb;
+  const dim3 grid = reduce_grid(N, V, &rpb, 8);
+  const double inv_count = 1.0 / ((double)V * (C / G));
+  og_gn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(x), sums, gamma, beta, cond_scale, cond_shift, A, B, mean_rstd,
+      reinterpret_cast<uint4*>(y), V, C, G, inv_count, eps, act, rpb);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_gn_act_bwd(const void* dy, const void* x, const float* A, const float* B, const float* S,
+                             const float* mean_rstd, const float* gamma, const float* beta, const float* cond_scale,
+                             int G, int act, const void* add, void* dx, float* dgamma, float* dbeta,
+                             float* dcond_scale, float* dcond_shift, float* dx_colsum, int N, int64_t V, int C,
+                             og_stream_t stream) {
+  OG_REQUIRE(dy && x && A && B && dx, "gn_act_bwd: null pointer");
+  OG_REQUIRE((S == nullptr) == (mean_rstd == nullptr), "gn_act_bwd: S and mean_rstd must both be given or both NULL");
+  OG_REQUIRE(C % 8 == 0 && C <= 2048 && G >= 1 && G <= 64 && C % G == 0 && (C / G) % 8 == 0,
+             "gn_act_bwd: need C%%8==0, C<=2048, G<=64, (C/G)%%8==0 (C=%d G=%d)", C, G);
+  long long rpb;
+  const dim3 grid = reduce_grid(N, V, &rpb, 6);
+  const double inv_M = 1.0 / ((double)V * (C / G));
+  og_gn_act_bwd_kernel<<<grid, 256, dx_colsum ? C * sizeof(float) : 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, S, mean_rstd, gamma, beta, cond_scale,
+      reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), dgamma, dbeta, dcond_scale, dcond_shift,
+      dx_colsum, V, C, G, inv_M, act, rpb);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;

@@ -279,7 +279,8 @@ class VideoResidualBlock(nn.Module):
         self.in_channels = in_channels
 
     def forward(self, inp: Tensor) -> Tensor:
-        if not self.has_down and inp.is_cuda:
+        fusable = all((c // self.main[0].num_groups) % 8 == 0 for c in (self.inp_channels, self.out_channels))
+        if not self.has_down and inp.is_cuda and fusable:
             # whole block as one autograd node: GroupNorm statistics / backward reductions come out of the GEMM
             # epilogues, the shortcut gradient is added inside the last apply pass. The statistics of the output
             # ride along on the tensor so that the next block's first GroupNorm needs no pass of its own.

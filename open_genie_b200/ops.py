@@ -319,10 +319,14 @@ class _GroupNormActFn(torch.autograd.Function):
         mr = torch.empty((B, G, 2), dtype=f32, device=dev)
         cs = None if cond_scale is None else cond_scale.detach().to(f32).contiguous()
         csh = None if cond_shift is None else cond_shift.detach().to(f32).contiguous()
-        _lib.call('og_gn_finalize', sums.data_ptr(), B, C, G, V, eps, _ptr(gamma), _ptr(beta), _ptr(cs), _ptr(csh),
-                  A.data_ptr(), Bc.data_ptr(), mr.data_ptr(), s)
         y = empty_internal(B, C, T, H, W, bf16, dev)
-        _lib.call('og_affine_act_fwd', xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), y.data_ptr(), B, V, C, act, s)
+        if (C // G) % 8 == 0:
+            _lib.call('og_gn_act_fwd', xi.data_ptr(), sums.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(cs), _ptr(csh), eps,
+                      G, act, y.data_ptr(), A.data_ptr(), Bc.data_ptr(), mr.data_ptr(), B, V, C, s)
+        else:
+            _lib.call('og_gn_finalize', sums.data_ptr(), B, C, G, V, eps, _ptr(gamma), _ptr(beta), _ptr(cs), _ptr(csh),
+                      A.data_ptr(), Bc.data_ptr(), mr.data_ptr(), s)
+            _lib.call('og_affine_act_fwd', xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), y.data_ptr(), B, V, C, act, s)
         ctx.cfg = (G, act, cond_scale is not None, cond_shift is not None)
         ctx.save_for_backward(xi, A, Bc, mr, gamma, beta, cs)
         return y
@@ -339,15 +343,21 @@ class _GroupNormActFn(torch.autograd.Function):
         S = torch.zeros((B, C, 2), dtype=f32, device=dev)
         _lib.call('og_affine_act_bwd_reduce', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), act,
                   S.data_ptr(), B, V, C, s)
-        Q = torch.empty((B, C), dtype=f32, device=dev)
-        R = torch.empty((B, C), dtype=f32, device=dev)
         dgamma = torch.zeros(C, dtype=f32, device=dev) if gamma is not None else None
         dbeta = torch.zeros(C, dtype=f32, device=dev) if beta is not None else None
         dcs = torch.empty((B, C), dtype=f32, device=dev) if has_cs else None
         dcsh = torch.empty((B, C), dtype=f32, device=dev) if has_csh else None
+        dx = None
+        if (C // G) % 8 == 0 and ctx.needs_input_grad[0]:
+            dx = empty_internal(B, C, T, H, W, bf16, dev)
+            _lib.call('og_gn_act_bwd', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), S.data_ptr(),
+                      mr.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(cs), G, act, None, dx.data_ptr(), _ptr(dgamma),
+                      _ptr(dbeta), _ptr(dcs), _ptr(dcsh), None, B, V, C, s)
+            return dx, dgamma, dbeta, dcs, dcsh, None, None, None
+        Q = torch.empty((B, C), dtype=f32, device=dev)
+        R = torch.empty((B, C), dtype=f32, device=dev)
         _lib.call('og_gn_bwd_finalize', S.data_ptr(), mr.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(cs), B, C, G, V,
                   Q.data_ptr(), R.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(dcs), _ptr(dcsh), s)
-        dx = None
         if ctx.needs_input_grad[0]:
             dx = empty_internal(B, C, T, H, W, bf16, dev)
             _lib.call('og_affine_act_bwd_apply', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(),
@@ -657,10 +667,9 @@ class _FfnFn(torch.autograd.Function):
         A = torch.empty((B, C), dtype=f32, device=dev)
         Bc = torch.empty((B, C), dtype=f32, device=dev)
         mr = torch.empty((B, G, 2), dtype=f32, device=dev)
-        _lib.call('og_gn_finalize', sums.data_ptr(), B, C, G, V, eps, gn_w.data_ptr(), gn_b.data_ptr(), None, None,
-                  A.data_ptr(), Bc.data_ptr(), mr.data_ptr(), s)
         hn = torch.empty_like(x)
-        _lib.call('og_affine_act_fwd', x.data_ptr(), A.data_ptr(), Bc.data_ptr(), hn.data_ptr(), B, V, C, 0, s)
+        _lib.call('og_gn_act_fwd', x.data_ptr(), sums.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), None, None, eps, G, 0,
+                  hn.data_ptr(), A.data_ptr(), Bc.data_ptr(), mr.data_ptr(), B, V, C, s)
         y = torch.empty_like(x)
         ws = _workspace(dev, B * V * C * 4)
         _conv_call('fwd', 2.0 * B * V * C * geom.k_main, 'og_conv3d_fwd', hn.data_ptr(), C, geom.kt, geom.kh, geom.kw,
@@ -690,15 +699,12 @@ class _FfnFn(torch.autograd.Function):
         _conv_call('wgrad', 2.0 * B * V * C * geom.k_main, 'og_conv3d_wgrad', dy.data_ptr(), C, hn.data_ptr(), C,
                    g.data_ptr(), g.shape[1], geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, B, T, H, W, s)
         dw = g.view(C, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
-        Q = torch.empty((B, C), dtype=f32, device=dev)
-        R = torch.empty((B, C), dtype=f32, device=dev)
         dgw = torch.zeros(C, dtype=f32, device=dev)
         dgb = torch.zeros(C, dtype=f32, device=dev)
-        _lib.call('og_gn_bwd_finalize', S.data_ptr(), mr.data_ptr(), gn_w.data_ptr(), gn_b.data_ptr(), None, B, C, G, V,
-                  Q.data_ptr(), R.data_ptr(), dgw.data_ptr(), dgb.data_ptr(), None, None, s)
         dx = torch.empty_like(x)
-        _lib.call('og_affine_act_bwd_apply', dh.data_ptr(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), Q.data_ptr(),
-                  R.data_ptr(), dy.data_ptr(), dx.data_ptr(), 0, B, V, C, s)
+        _lib.call('og_gn_act_bwd', dh.data_ptr(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), S.data_ptr(), mr.data_ptr(),
+                  gn_w.data_ptr(), gn_b.data_ptr(), None, G, 0, dy.data_ptr(), dx.data_ptr(), dgw.data_ptr(),
+                  dgb.data_ptr(), None, None, None, B, V, C, s)
         return dx, dgw, dgb, dw, None, None, None, None
 
 
@@ -819,10 +825,9 @@ class _ResBlockFn(torch.autograd.Function):
         A1, B1, A2, B2 = coef[0, 0, :, :C0], coef[0, 1, :, :C0], coef[1, 0, :, :C1], coef[1, 1, :, :C1]
         A1, B1 = torch.empty((B, C0), dtype=f32, device=dev), torch.empty((B, C0), dtype=f32, device=dev)
         A2, B2 = torch.empty((B, C1), dtype=f32, device=dev), torch.empty((B, C1), dtype=f32, device=dev)
-        _lib.call('og_gn_finalize', x_sums.data_ptr(), B, C0, G, V, eps, g1w.data_ptr(), g1b.data_ptr(), None, None,
-                  A1.data_ptr(), B1.data_ptr(), mr[0].data_ptr(), s)
         a1 = empty_internal(B, C0, T, H, W, bf16, dev)
-        _lib.call('og_affine_act_fwd', xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), a1.data_ptr(), B, V, C0, 1, s)
+        _lib.call('og_gn_act_fwd', xi.data_ptr(), x_sums.data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, None, eps, G, 1,
+                  a1.data_ptr(), A1.data_ptr(), B1.data_ptr(), mr[0].data_ptr(), B, V, C0, s)
         ws = _workspace(dev, B * V * C1 * 4)
         fuse_stats = G == 1 and FUSE_STATS
         sums2 = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
@@ -833,10 +838,9 @@ class _ResBlockFn(torch.autograd.Function):
                    sums2.data_ptr() if fuse_stats else None, s)
         if not fuse_stats:
             _lib.call('og_gn_stats', h1.data_ptr(), B, V, C1, G, sums2.data_ptr(), s)
-        _lib.call('og_gn_finalize', sums2.data_ptr(), B, C1, G, V, eps, g2w.data_ptr(), g2b.data_ptr(), None, None,
-                  A2.data_ptr(), B2.data_ptr(), mr[1].data_ptr(), s)
         a2 = empty_internal(B, C1, T, H, W, bf16, dev)
-        _lib.call('og_affine_act_fwd', h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), a2.data_ptr(), B, V, C1, 1, s)
+        _lib.call('og_gn_act_fwd', h1.data_ptr(), sums2.data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, None, eps, G, 1,
+                  a2.data_ptr(), A2.data_ptr(), B2.data_ptr(), mr[1].data_ptr(), B, V, C1, s)
         y = empty_internal(B, C1, T, H, W, bf16, dev)
         y_sums = torch.zeros((B, 1, 2), dtype=torch.float64, device=dev)
         _conv_call('fwd', 2.0 * B * V * C1 * (geom2.k_main + C0), 'og_conv3d_fwd', a2.data_ptr(), C1, geom2.kt, geom2.kh,
@@ -884,15 +888,12 @@ class _ResBlockFn(torch.autograd.Function):
         if not FUSE_RED:
             _lib.call('og_affine_act_bwd_reduce', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1,
                       S2.data_ptr(), B, V, C1, s)
-        Q2, R2 = torch.empty((B, C1), dtype=f32, device=dev), torch.empty((B, C1), dtype=f32, device=dev)
-        dg2w, dg2b = torch.zeros(C1, dtype=f32, device=dev), torch.zeros(C1, dtype=f32, device=dev)
-        _lib.call('og_gn_bwd_finalize', S2.data_ptr(), mr[1].data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, B, C1, G, V,
-                  Q2.data_ptr(), R2.data_ptr(), dg2w.data_ptr(), dg2b.data_ptr(), None, None, s)
+        small = torch.zeros((3, C1), dtype=f32, device=dev)              # dgamma2, dbeta2, db1 in one fill
+        dg2w, dg2b, db1 = small[0], small[1], small[2]
         d_h1 = empty_internal(B, C1, T, H, W, bf16, dev)
-        _lib.call('og_affine_act_bwd_apply', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), Q2.data_ptr(),
-                  R2.data_ptr(), None, d_h1.data_ptr(), 1, B, V, C1, s)
-        db1 = torch.zeros(C1, dtype=f32, device=dev)
-        _lib.call('og_colsum', d_h1.data_ptr(), B * V, C1, C1, db1.data_ptr(), s)
+        _lib.call('og_gn_act_bwd', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), S2.data_ptr(),
+                  mr[1].data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, G, 1, None, d_h1.data_ptr(), dg2w.data_ptr(),
+                  dg2b.data_ptr(), None, None, db1.data_ptr() if has_b1 else None, B, V, C1, s)
         dw1 = wgrad(d_h1, C1, a1, C0, geom1)
         dx = None
         dg1w, dg1b = torch.zeros(C0, dtype=f32, device=dev), torch.zeros(C0, dtype=f32, device=dev)
@@ -911,13 +912,11 @@ class _ResBlockFn(torch.autograd.Function):
         _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
                    geom2.k_main, 1, 1, 1, 0, 0, 0, dx_res.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
                    None, None, None, 0, None, s)
-        Q1, R1 = torch.empty((B, C0), dtype=f32, device=dev), torch.empty((B, C0), dtype=f32, device=dev)
-        _lib.call('og_gn_bwd_finalize', S1.data_ptr(), mr[0].data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, B, C0, G, V,
-                  Q1.data_ptr(), R1.data_ptr(), dg1w.data_ptr(), dg1b.data_ptr(), None, None, s)
-        if ctx.needs_input_grad[0]:
-            dx = empty_internal(B, C0, T, H, W, bf16, dev)
-            _lib.call('og_affine_act_bwd_apply', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(),
-                      Q1.data_ptr(), R1.data_ptr(), dx_res.data_ptr(), dx.data_ptr(), 1, B, V, C0, s)
+        # (the input gradient is always produced: its pass is also what emits dgamma1 / dbeta1)
+        dx = empty_internal(B, C0, T, H, W, bf16, dev)
+        _lib.call('og_gn_act_bwd', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), S1.data_ptr(),
+                  mr[0].data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, G, 1, dx_res.data_ptr(), dx.data_ptr(),
+                  dg1w.data_ptr(), dg1b.data_ptr(), None, None, None, B, V, C0, s)
         return (dx, None, dg1w, dg1b, dw1, db1 if has_b1 else None, dg2w, dg2b, dw2, db2 if has_b2 else None, dwres,
                 (db2.clone() if has_b2 else db2) if has_bres else None, None, None, None, None, None, None)
 
