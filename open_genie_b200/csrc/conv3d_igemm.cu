@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   float* red_s = coef_s + 512;                                            // [256][2] column sums of the current tile
   double* stat_s = reinterpret_cast<double*>(red_s + 512);                // [2]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int num_m_super = (p.num_m_tiles + p.m_sub - 1) / p.m_sub;
   const int total_tiles = num_m_super * p.num_n_tiles * p.splits;  // work items
@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // (all 32 lanes run the loop converged; one elected lane issues — see elect_one() in og_ptx.cuh)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
@@ -171,17 +172,22 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-          tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n0);
-          if (p.m_sub == 2)
-            tma_load_5d(sa + kABytes, mapA, &full[stage], cb * kBlockK, tc1.w0 + dw, tc1.h0 + dh, tc1.t0 + dt, tc1.n0);
-          if (!p.b_mn_major) {
-            tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
-          } else {
-            // w[co][tap][ci] as (ci, tap, co): one (64 ci, 1 tap, 64 co) box per 64-wide N panel
-            for (int pp = 0; pp < p.block_n / 64; ++pp)
-              tma_load_3d(sb + pp * (64 * 128), &mapB, &full[stage], n_tile * p.block_n + pp * 64, tap, cb * kBlockK);
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n0);
+            if (p.m_sub == 2)
+              tma_load_5d(sa + kABytes, mapA, &full[stage], cb * kBlockK, tc1.w0 + dw, tc1.h0 + dh, tc1.t0 + dt,
+                          tc1.n0);
+            if (!p.b_mn_major) {
+              tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
+            } else {
+              // w[co][tap][ci] as (ci, tap, co): one (64 ci, 1 tap, 64 co) box per 64-wide N panel
+              for (int pp = 0; pp < p.block_n / 64; ++pp)
+                tma_load_3d(sb + pp * (64 * 128), &mapB, &full[stage], n_tile * p.block_n + pp * 64, tap,
+                            cb * kBlockK);
+            }
           }
+          __syncwarp();
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0u, (uint32_t)p.b_mn_major);
       int stage = 0;
       uint32_t phase = 0;
@@ -225,28 +231,32 @@ __global__ void __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + a_bytes;
-          for (int ms = 0; ms < p.m_sub; ++ms) {
+          if (elect_one()) {
+            for (int ms = 0; ms < p.m_sub; ++ms) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // A: K-major, 128-byte rows, 8-row groups 1024 B apart; advance 16 elements = 32 B inside the row
-              const uint64_t adesc = umma_smem_desc_sw128(a_addr + ms * kABytes + k * 32, 16, 1024);
-              uint64_t bdesc;
-              if (!p.b_mn_major) {
-                bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-              } else {
-                // B: MN-major panels [block_n/64][64 k-rows][128 B]; 16 k-rows = 2048 B; panel stride 8192 B
-                bdesc = umma_smem_desc_sw128(b_addr + k * 2048, 64 * 128, 1024);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // A: K-major, 128-byte rows, 8-row groups 1024 B apart; advance 16 elements = 32 B inside the row
+                const uint64_t adesc = umma_smem_desc_sw128(a_addr + ms * kABytes + k * 32, 16, 1024);
+                uint64_t bdesc;
+                if (!p.b_mn_major) {
+                  bdesc = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                } else {
+                  // B: MN-major panels [block_n/64][64 k-rows][128 B]; 16 k-rows = 2048 B; panel stride 8192 B
+                  bdesc = umma_smem_desc_sw128(b_addr + k * 2048, 64 * 128, 1024);
+                }
+                umma_bf16_ss(d_tmem + ms * p.block_n, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
               }
-              umma_bf16_ss(d_tmem + ms * p.block_n, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
+            umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
   uint64_t* tmem_full = bars + 4 * kWMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kWMaxStages + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int co0 = blockIdx.x * 128;
   const int ci0 = blockIdx.y * p.block_n;
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(kWThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      // whole warp runs the loop converged; one elected lane issues (see elect_one() in og_ptx.cuh)
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       // The producer is ONE thread: keep its per-k-step instruction count tiny (no divisions in the loop).
@@ -122,9 +123,12 @@ __global__ void __launch_bounds__(kWThreads, 1)
       for (int ks = ks_begin; ks < ks_end; ++ks) {
         const int n = tn << p.bn_log2, w0 = tw << p.bw_log2, h0 = th << p.bh_log2, t0 = tt << p.bt_log2;
         mbar_wait(&empty_a[sa], pha ^ 1);
-        mbar_expect_tx(&full_a[sa], kWABytes);
-        tma_load_5d(smem_a + sa * kWABytes, &mapDY, &full_a[sa], co0, w0, h0, t0, n);
-        tma_load_5d(smem_a + sa * kWABytes + kPanelBytes, &mapDY, &full_a[sa], co0 + 64, w0, h0, t0, n);
+        if (elect_one()) {
+          mbar_expect_tx(&full_a[sa], kWABytes);
+          tma_load_5d(smem_a + sa * kWABytes, &mapDY, &full_a[sa], co0, w0, h0, t0, n);
+          tma_load_5d(smem_a + sa * kWABytes + kPanelBytes, &mapDY, &full_a[sa], co0 + 64, w0, h0, t0, n);
+        }
+        __syncwarp();
         if (++sa == p.a_stages) {
           sa = 0;
           pha ^= 1;
@@ -134,16 +138,19 @@ __global__ void __launch_bounds__(kWThreads, 1)
           if (j < ntap) {
             const int nt = (ntap - j) < 2 ? 1 : 2;
             mbar_wait(&empty_b[sb], phb ^ 1);
-            mbar_expect_tx(&full_b[sb], (uint32_t)(nt * tap_bytes));
-            uint8_t* dst = smem_b + sb * b_bytes;
+            if (elect_one()) {
+              mbar_expect_tx(&full_b[sb], (uint32_t)(nt * tap_bytes));
+              uint8_t* dst = smem_b + sb * b_bytes;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              if (u < nt) {
-                for (int pp = 0; pp < panels; ++pp)
-                  tma_load_5d(dst + u * tap_bytes + pp * kPanelBytes, &mapX, &full_b[sb], ci0 + pp * 64,
-                              w0 + off_w[j + u], h0 + off_h[j + u], t0 + off_t[j + u], n);
+              for (int u = 0; u < 2; ++u) {
+                if (u < nt) {
+                  for (int pp = 0; pp < panels; ++pp)
+                    tma_load_5d(dst + u * tap_bytes + pp * kPanelBytes, &mapX, &full_b[sb], ci0 + pp * 64,
+                                w0 + off_w[j + u], h0 + off_h[j + u], t0 + off_t[j + u], n);
+                }
               }
             }
+            __syncwarp();
             if (++sb == p.b_stages) {
               sb = 0;
               phb ^= 1;
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t amn = (p.dbg & 1) ? 0u : 1u, bmn = (p.dbg & 2) ? 0u : 1u;
       const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)p.block_n, amn, bmn);
       const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * p.block_n), amn, bmn);
@@ -180,26 +187,30 @@ __global__ void __launch_bounds__(kWThreads, 1)
           const uint32_t b_addr = smem_u32(smem_b + sb * b_bytes);
           const uint32_t d_tmem = tmem_base + j * p.block_n;
           const uint32_t idesc = (ntap - j >= 2) ? idesc2 : idesc1;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kVox / 16; ++k) {
-            // MN-major panels [panel][64 k-rows][128 B]: 16 k-rows = 2048 B, panel stride = 8192 B
-            const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, kPanelBytes, 1024);
-            const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, kPanelBytes, 1024);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (ks > ks_begin || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kVox / 16; ++k) {
+              // MN-major panels [panel][64 k-rows][128 B]: 16 k-rows = 2048 B, panel stride = 8192 B
+              const uint64_t adesc = umma_smem_desc_sw128(a_addr + k * 2048, kPanelBytes, 1024);
+              const uint64_t bdesc = umma_smem_desc_sw128(b_addr + k * 2048, kPanelBytes, 1024);
+              umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (ks > ks_begin || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_b[sb]);
           }
-          umma_commit(&empty_b[sb]);
+          __syncwarp();
           if (++sb == p.b_stages) {
             sb = 0;
             phb ^= 1;
           }
         }
-        umma_commit(&empty_a[sa]);
+        if (elect_one()) umma_commit(&empty_a[sa]);
+        __syncwarp();
         if (++sa == p.a_stages) {
           sa = 0;
           pha ^= 1;
         }
       }
-      umma_commit(tmem_full);
+      if (elect_one()) umma_commit(tmem_full);
     }
     __syncwarp();
   } else {

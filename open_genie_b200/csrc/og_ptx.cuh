@@ -16,6 +16,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
+// Warp index as a value the compiler can prove warp-uniform (threadIdx.x >> 5 alone is not), and a
+// one-lane election. Producer / MMA-issuer warps run their loops with ALL lanes converged and predicate only
+// the TMA / tcgen05 instruction on elect_one(): coordinates, addresses and barrier pointers then live in
+// uniform registers. Branching the whole role on `lane == 0` instead makes every operand a per-thread value
+// and costs ~10 R2UR/ELECT round trips per TMA — enough to make a single producer thread the bottleneck.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
