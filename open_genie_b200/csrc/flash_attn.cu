@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kFaThreads, 1)
   uint64_t* pv_ready = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   int id = blockIdx.x;
   const int qt = id % p.q_tiles;
   id /= p.q_tiles;
@@ -89,21 +89,27 @@ __global__ void __launch_bounds__(kFaThreads, 1)
   const uint32_t tPV = tmem_base + 128;  // 64 columns
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_3d(sQ, &mapQ, q_full, h * kD, q0, seq);
+    {  // converged warp, one elected lane issues (og_ptx.cuh: elect_one)
+      if (elect_one()) {
+        mbar_expect_tx(q_full, kTileBytes);
+        tma_load_3d(sQ, &mapQ, q_full, h * kD, q0, seq);
+      }
+      __syncwarp();
       for (int j = 0; j < p.kv_tiles; ++j) {
         const int st = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
-        tma_load_3d(sKV + st * 2 * kTileBytes, &mapK, &kv_full[st], h * kD, j * kTile, seq);
-        tma_load_3d(sKV + st * 2 * kTileBytes + kTileBytes, &mapV, &kv_full[st], h * kD, j * kTile, seq);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[st], 2 * kTileBytes);
+          tma_load_3d(sKV + st * 2 * kTileBytes, &mapK, &kv_full[st], h * kD, j * kTile, seq);
+          tma_load_3d(sKV + st * 2 * kTileBytes + kTileBytes, &mapV, &kv_full[st], h * kD, j * kTile, seq);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0u, 0u);   // S = Q K^T : both K-major
       const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0u, 1u);   // PV = P V  : A K-major, B MN-major
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
@@ -120,11 +126,14 @@ __global__ void __launch_bounds__(kFaThreads, 1)
             tc_fence_after();
           }
           const uint32_t k_addr = smem_u32(sKV + st * 2 * kTileBytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
-            umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(s_ready);
+            for (int k = 0; k < kD / 16; ++k)
+              umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(s_ready);
+          }
+          __syncwarp();
         }
         if (j > 0) {
           // PV_{j-1} = P_{j-1} V_{j-1}
@@ -134,12 +143,15 @@ __global__ void __launch_bounds__(kFaThreads, 1)
             tc_fence_after();
           }
           const uint32_t v_addr = smem_u32(sKV + st * 2 * kTileBytes + kTileBytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kTile / 16; ++k)
-            umma_bf16_ss(tPV, umma_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                         umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_pv, k > 0 ? 1u : 0u);
-          umma_commit(pv_ready);
-          umma_commit(&kv_empty[st]);
+            for (int k = 0; k < kTile / 16; ++k)
+              umma_bf16_ss(tPV, umma_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                           umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_pv, k > 0 ? 1u : 0u);
+            umma_commit(pv_ready);
+            umma_commit(&kv_empty[st]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(kFaThreads, 1)
   uint64_t* acc_ready = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   int id = blockIdx.x;
   const int own = id % p.tiles;  // MODE 0: kv tile ; MODE 1: q tile
   id /= p.tiles;
@@ -335,32 +347,38 @@ __global__ void __launch_bounds__(kFaThreads, 1)
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tAcc0 = tmem_base + 256, tAcc1 = tmem_base + 320;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(fix_full, 2 * kTileBytes);
-      if (MODE == 0) {
-        tma_load_3d(sFix, &mapK, fix_full, h * kD, own * kTile, seq);
-        tma_load_3d(sFix + kTileBytes, &mapV, fix_full, h * kD, own * kTile, seq);
-      } else {
-        tma_load_3d(sFix, &mapQ, fix_full, h * kD, own * kTile, seq);
-        tma_load_3d(sFix + kTileBytes, &mapDO, fix_full, h * kD, own * kTile, seq);
+    {
+      if (elect_one()) {
+        mbar_expect_tx(fix_full, 2 * kTileBytes);
+        if (MODE == 0) {
+          tma_load_3d(sFix, &mapK, fix_full, h * kD, own * kTile, seq);
+          tma_load_3d(sFix + kTileBytes, &mapV, fix_full, h * kD, own * kTile, seq);
+        } else {
+          tma_load_3d(sFix, &mapQ, fix_full, h * kD, own * kTile, seq);
+          tma_load_3d(sFix + kTileBytes, &mapDO, fix_full, h * kD, own * kTile, seq);
+        }
       }
+      __syncwarp();
       for (int it = 0; it < p.tiles; ++it) {
         const int st = it & 1;
         mbar_wait(&str_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&str_full[st], 2 * kTileBytes);
-        uint8_t* d = sStr + st * 2 * kTileBytes;
-        if (MODE == 0) {
-          tma_load_3d(d, &mapQ, &str_full[st], h * kD, it * kTile, seq);
-          tma_load_3d(d + kTileBytes, &mapDO, &str_full[st], h * kD, it * kTile, seq);
-        } else {
-          tma_load_3d(d, &mapK, &str_full[st], h * kD, it * kTile, seq);
-          tma_load_3d(d + kTileBytes, &mapV, &str_full[st], h * kD, it * kTile, seq);
+        if (elect_one()) {
+          mbar_expect_tx(&str_full[st], 2 * kTileBytes);
+          uint8_t* d = sStr + st * 2 * kTileBytes;
+          if (MODE == 0) {
+            tma_load_3d(d, &mapQ, &str_full[st], h * kD, it * kTile, seq);
+            tma_load_3d(d + kTileBytes, &mapDO, &str_full[st], h * kD, it * kTile, seq);
+          } else {
+            tma_load_3d(d, &mapK, &str_full[st], h * kD, it * kTile, seq);
+            tma_load_3d(d + kTileBytes, &mapV, &str_full[st], h * kD, it * kTile, seq);
+          }
         }
+        __syncwarp();
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0u, 0u);  // S, dP: both operands K-major
       const uint32_t idesc_mm = umma_idesc_bf16(128, 64, 1u, 1u);   // dV, dK: A (P / dS transposed) and B MN-major
       const uint32_t idesc_km = umma_idesc_bf16(128, 64, 0u, 1u);   // dQ: A = dS K-major, B = K MN-major
@@ -378,15 +396,18 @@ __global__ void __launch_bounds__(kFaThreads, 1)
           const uint32_t fixa = smem_u32(sFix), stra = smem_u32(sStr + st * 2 * kTileBytes);
           const uint32_t q_addr = MODE == 0 ? stra : fixa, do_addr = q_addr + kTileBytes;
           const uint32_t k_addr = MODE == 0 ? fixa : stra, v_addr = k_addr + kTileBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
-            umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+            for (int k = 0; k < kD / 16; ++k)
+              umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
-            umma_bf16_ss(tDP, umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
-                         umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
-          umma_commit(sd_ready);
+            for (int k = 0; k < kD / 16; ++k)
+              umma_bf16_ss(tDP, umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                           umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+            umma_commit(sd_ready);
+          }
+          __syncwarp();
         }
         if (it > 0) {
           const int jj = it - 1, st = jj & 1;
@@ -395,7 +416,8 @@ __global__ void __launch_bounds__(kFaThreads, 1)
             tc_fence_after();
           }
           const uint32_t fixa = smem_u32(sFix), stra = smem_u32(sStr + st * 2 * kTileBytes);
-          if (MODE == 0) {
+          if (!elect_one()) {
+          } else if (MODE == 0) {
             const uint32_t q_addr = stra, do_addr = stra + kTileBytes;
 #pragma unroll
             for (int k = 0; k < kTile / 16; ++k) {  // K dim = 128 query rows, 16 per MMA
@@ -411,11 +433,13 @@ __global__ void __launch_bounds__(kFaThreads, 1)
               umma_bf16_ss(tAcc0, umma_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
                            umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_km, (jj > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&str_empty[st]);
+          __syncwarp();
+          if (elect_one()) umma_commit(&str_empty[st]);
+          __syncwarp();
           (void)fixa;
         }
       }
-      umma_commit(acc_ready);
+      if (elect_one()) umma_commit(acc_ready);
     }
     __syncwarp();
   } else {

@@ -329,12 +329,10 @@ __global__ void og_colsum_kernel(const __nv_bfloat16* __restrict__ x, long long 
 // range with 4 independent 16-byte loads in flight, then shared atomics and one global atomic per channel.
 __global__ void __launch_bounds__(256) og_colsum_vec_kernel(const uint4* __restrict__ x, long long rows, int C, int ld,
                                                             long long rows_per_block, float* __restrict__ out) {
-  extern __shared__ float sh[];  // [cw]
+  __shared__ float part[256 * 8];  // per-thread partial column sums
   const int c0 = blockIdx.y * 2048;
   const int cw = (ld - c0 < 2048) ? ld - c0 : 2048;  // columns of this block
   const int cvs = cw >> 3, ldv = ld >> 3;
-  for (int i = threadIdx.x; i < cw; i += 256) sh[i] = 0.f;
-  __syncthreads();
   const int lanes = 256 / cvs;
   const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -369,11 +367,18 @@ __global__ void __launch_bounds__(256) og_colsum_vec_kernel(const uint4* __restr
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&sh[cv * 8 + i], acc[i]);
+    for (int i = 0; i < 8; ++i) part[threadIdx.x * 8 + i] = acc[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[threadIdx.x * 8 + i] = 0.f;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < cw; c += 256)
-    if (c0 + c < C) atomicAdd(&out[c0 + c], sh[c]);
+  // thread index == rl * cvs + cv: sum the row lanes of each column (no contended shared atomics)
+  for (int c = threadIdx.x; c < cw; c += 256) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += part[(l * cvs + (c >> 3)) * 8 + (c & 7)];
+    if (c0 + c < C) atomicAdd(&out[c0 + c], a);
+  }
 }
 
 // copy [rows][cs] -> [rows][cd] (cd >= cs zero padded, or cd < cs truncating); src f32 or bf16, dst bf16
@@ -577,8 +582,7 @@ extern "C" int og_colsum(const void* x, int64_t rows, int C, int ld, float* out,
     if (want < 1) want = 1;
     const long long rpb = ((groups + want - 1) / want) * 64;
     dim3 grid((unsigned)((rows + rpb - 1) / rpb), col_blocks);
-    const int cw = ld < 2048 ? ld : 2048;
-    og_colsum_vec_kernel<<<grid, 256, cw * sizeof(float), (cudaStream_t)stream>>>((const uint4*)x, rows, C, ld, rpb, out);
+    og_colsum_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, rows, C, ld, rpb, out);
   } else {
     const unsigned blocks = (unsigned)((rows + 255) / 256);
     og_colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, ld, out);

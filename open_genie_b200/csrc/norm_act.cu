@@ -26,6 +26,19 @@ __device__ __forceinline__ float sigmoid_f(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
   return fmaf(t, 0.5f, 0.5f);
 }
+__device__ __forceinline__ float tanh_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+// With h = pre/2 and t = tanh(h):  silu(pre) = h (1 + t),  silu'(pre) = (1 + w)/2 with w = t + h (1 - t^2).
+// The hot loops fold the 1/2 into the per-channel scale/shift (h = x*A/2 + B/2) and into the output scale, which
+// leaves 3 operations per element forward and 5 backward around the single MUFU op.
+__device__ __forceinline__ float silu_from_half(float h) { return fmaf(h, tanh_fast(h), h); }
+__device__ __forceinline__ float silu_grad2_from_half(float h) {  // 2 * silu'(2h) - 1  (= w above)
+  const float t = tanh_fast(h);
+  return fmaf(h, fmaf(-t, t, 1.f), t);
+}
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float silu_grad_f(float x) {
   const float s = sigmoid_f(x);
@@ -58,7 +71,7 @@ static constexpr int kStatRows = 256;  // granularity of the row ranges handed t
 // grid (blocks_per_sample, N); each block owns a contiguous row range of one sample and keeps fp32 partial
 // sums in registers over the whole range (4 independent 16-byte loads in flight per thread), then one
 // shared-memory and one global fp64 atomic per group.
-__global__ void __launch_bounds__(256) og_gn_stats_kernel(const uint4* __restrict__ x, long long V, int C, int G,
+__global__ void __launch_bounds__(256, 6) og_gn_stats_kernel(const uint4* __restrict__ x, long long V, int C, int G,
                                                           long long rows_per_block, double* __restrict__ sums) {
   const int cvs = C >> 3;  // channel vectors per row (host guarantees cvs <= 256)
   const int n = blockIdx.y;
@@ -69,16 +82,17 @@ __global__ void __launch_bounds__(256) og_gn_stats_kernel(const uint4* __restric
   __syncthreads();
   const int lanes = 256 / cvs;
   const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
+  float ts = 0.f, tss = 0.f;
   if (rl < lanes && r_begin < V) {
     const uint4* base = x + (long long)n * V * cvs + cv;
     float s = 0.f, ss = 0.f;
     long long r = r_begin + rl;
-    for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
-      uint4 u[4];
+    for (; r + 7LL * lanes < r_end; r += 8LL * lanes) {
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(base + (r + (long long)k * lanes) * cvs);
+      for (int k = 0; k < 8; ++k) u[k] = __ldg(base + (r + (long long)k * lanes) * cvs);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         float f[8];
         unpack8(u[k], f);
 #pragma unroll
@@ -97,9 +111,28 @@ __global__ void __launch_bounds__(256) og_gn_stats_kernel(const uint4* __restric
         ss = fmaf(f[i], f[i], ss);
       }
     }
-    const int g = (cv * 8) / (C / G);
-    atomicAdd(&sh[2 * g], (double)s);
-    atomicAdd(&sh[2 * g + 1], (double)ss);
+    if (G > 1) {
+      const int g = (cv * 8) / (C / G);
+      atomicAdd(&sh[2 * g], (double)s);
+      atomicAdd(&sh[2 * g + 1], (double)ss);
+    } else {
+      ts = s;
+      tss = ss;
+    }
+  }
+  if (G == 1) {
+    // one group: shuffle-reduce per warp, 8 partials per block (256 threads hammering one shared fp64 atomic
+    // serialise into a CAS loop that costs more than the whole streaming pass)
+    double ds = (double)ts, dss = (double)tss;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, off);
+      dss += __shfl_xor_sync(0xffffffffu, dss, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sh[0], ds);
+      atomicAdd(&sh[1], dss);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&sums[(long long)n * G * 2 + i], sh[i]);
@@ -169,7 +202,7 @@ __global__ void __launch_bounds__(256) og_affine_act_fwd_kernel(const uint4* __r
 // backward reduce: S[n][c] = (sum_v dpre, sum_v dpre * x), dpre = dy * act'(x*A+B)
 // grid (chunks, N), block 256; same thread mapping as the stats kernel.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     og_affine_act_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                     const float* __restrict__ A, const float* __restrict__ B, long long V, int C,
                                     int act, long long rows_per_block, float* __restrict__ S) {
@@ -177,61 +210,65 @@ __global__ void __launch_bounds__(256)
   const int n = blockIdx.y;
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
   const long long r_end = (r_begin + rows_per_block < V) ? r_begin + rows_per_block : V;
-  extern __shared__ float shs[];  // [C][2]
-  for (int i = threadIdx.x; i < 2 * C; i += 256) shs[i] = 0.f;
-  __syncthreads();
+  __shared__ float part[256 * 16];  // per-thread partial sums (s1[8], s2[8])
   const int lanes = 256 / cvs;
   const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
   if (rl < lanes && r_begin < V) {
+    // act: h = pre/2 = x*(A/2) + B/2 and e = dy (1 + w) = 2 dpre (see silu_grad2_from_half); sums halved at the end
     float av[8], bv[8];
+    const float cs = act ? 0.5f : 1.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      av[k] = A[(long long)n * C + cv * 8 + k];
-      bv[k] = B[(long long)n * C + cv * 8 + k];
+      av[k] = cs * A[(long long)n * C + cv * 8 + k];
+      bv[k] = cs * B[(long long)n * C + cv * 8 + k];
     }
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long base = (long long)n * V * cvs + cv;
+    auto accum = [&](const uint4& uxv, const uint4& udv) {
+      float fx[8], fd[8];
+      unpack8(uxv, fx);
+      unpack8(udv, fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float e = act ? fmaf(fd[k], silu_grad2_from_half(fmaf(fx[k], av[k], bv[k])), fd[k]) : fd[k];
+        s1[k] += e;
+        s2[k] = fmaf(e, fx[k], s2[k]);
+      }
+    };
     long long r = r_begin + rl;
-    for (; r + (long long)lanes < r_end; r += 2LL * lanes) {
-      const uint4 ux0 = __ldg(x + base + r * cvs), ud0 = __ldg(dy + base + r * cvs);
-      const uint4 ux1 = __ldg(x + base + (r + lanes) * cvs), ud1 = __ldg(dy + base + (r + lanes) * cvs);
-      float fx[8], fd[8];
-      unpack8(ux0, fx);
-      unpack8(ud0, fd);
+    for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
+      uint4 ux[4], ud[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
-        s1[k] += dpre;
-        s2[k] = fmaf(dpre, fx[k], s2[k]);
+      for (int j = 0; j < 4; ++j) {
+        ux[j] = __ldg(x + base + (r + (long long)j * lanes) * cvs);
+        ud[j] = __ldg(dy + base + (r + (long long)j * lanes) * cvs);
       }
-      unpack8(ux1, fx);
-      unpack8(ud1, fd);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
-        s1[k] += dpre;
-        s2[k] = fmaf(dpre, fx[k], s2[k]);
-      }
+      for (int j = 0; j < 4; ++j) accum(ux[j], ud[j]);
     }
-    for (; r < r_end; r += lanes) {
-      float fx[8], fd[8];
-      unpack8(__ldg(x + base + r * cvs), fx);
-      unpack8(__ldg(dy + base + r * cvs), fd);
+    for (; r < r_end; r += lanes) accum(__ldg(x + base + r * cvs), __ldg(dy + base + r * cvs));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
-        s1[k] += dpre;
-        s2[k] = fmaf(dpre, fx[k], s2[k]);
-      }
+    for (int k = 0; k < 8; ++k) {
+      s1[k] *= cs;
+      s2[k] *= cs;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&shs[2 * (cv * 8 + k)], s1[k]);
-      atomicAdd(&shs[2 * (cv * 8 + k) + 1], s2[k]);
+      part[threadIdx.x * 16 + k] = s1[k];
+      part[threadIdx.x * 16 + 8 + k] = s2[k];
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) part[threadIdx.x * 16 + k] = 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&S[(long long)n * C * 2 + i], shs[i]);
+  // thread index == rl * cvs + cv: sum the row lanes of every channel (no contended shared atomics)
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const int c = i >> 1, which = i & 1;
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += part[(l * cvs + (c >> 3)) * 16 + which * 8 + (c & 7)];
+    atomicAdd(&S[(long long)n * C * 2 + i], a);
+  }
 }
 
 // backward finalize: one block per sample n, 256 threads.
@@ -363,6 +400,13 @@ __global__ void __launch_bounds__(256, 4)
       }
     }
   }
+  if (act) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      av[k] *= 0.5f;
+      bv[k] *= 0.5f;
+    }
+  }
   const long long base = (long long)n * V * cvs + cv;
   long long r = r_begin + rl;
   for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
@@ -375,8 +419,8 @@ __global__ void __launch_bounds__(256, 4)
       unpack8(u[j], f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float pre = fmaf(f[k], av[k], bv[k]);
-        f[k] = act ? silu_f(pre) : pre;
+        const float h = fmaf(f[k], av[k], bv[k]);
+        f[k] = act ? silu_from_half(h) : h;
       }
       y[base + (r + (long long)j * lanes) * cvs] = pack8(f);
     }
@@ -386,8 +430,8 @@ __global__ void __launch_bounds__(256, 4)
     unpack8(__ldg(x + base + r * cvs), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float pre = fmaf(f[k], av[k], bv[k]);
-      f[k] = act ? silu_f(pre) : pre;
+      const float h = fmaf(f[k], av[k], bv[k]);
+      f[k] = act ? silu_from_half(h) : h;
     }
     y[base + r * cvs] = pack8(f);
   }
@@ -415,10 +459,10 @@ __global__ void __launch_bounds__(256, 3)
   const int cv = threadIdx.x % cvs, rl = threadIdx.x / cvs;
   const int cpg = C / G;
   __shared__ double m1s[64], m2s[64];
-  extern __shared__ float cs_s[];  // [C] column sums of dx (only when dx_colsum)
+  extern __shared__ float cs_s[];  // [256][8] per-thread column sums of dx (only when dx_colsum)
   for (int i = threadIdx.x; i < G; i += 256) m1s[i] = m2s[i] = 0.0;
   if (dx_colsum)
-    for (int i = threadIdx.x; i < C; i += 256) cs_s[i] = 0.f;
+    for (int i = threadIdx.x; i < 256 * 8; i += 256) cs_s[i] = 0.f;
   __syncthreads();
   if (S) {
     const bool warp_uniform = (cpg % 32) == 0;  // then C % 32 == 0 and a warp's 32 channels share one group
@@ -464,6 +508,13 @@ __global__ void __launch_bounds__(256, 3)
       av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
       bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
     }
+    if (act) {  // h = pre/2 and e = 2 dpre below: fold both halves into the coefficients
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        av[k] *= 0.5f;
+        bv[k] *= 0.5f;
+      }
+    }
     float q = 0.f, rr = 0.f;
     if (S) {
       const int g = (cv * 8) / cpg;
@@ -486,8 +537,8 @@ __global__ void __launch_bounds__(256, 3)
       if (add) unpack8(ua, fa);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], av[k], bv[k])) : fd[k];
-        float v = fmaf(av[k], dpre, fmaf(qv[k], fx[k], rv[k]));
+        const float e = act ? fmaf(fd[k], silu_grad2_from_half(fmaf(fx[k], av[k], bv[k])), fd[k]) : fd[k];
+        float v = fmaf(av[k], e, fmaf(qv[k], fx[k], rv[k]));
         if (add) v += fa[k];
         out[k] = v;
         cs[k] += v;
@@ -514,12 +565,16 @@ __global__ void __launch_bounds__(256, 3)
     }
     if (dx_colsum) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(&cs_s[cv * 8 + k], cs[k]);
+      for (int k = 0; k < 8; ++k) cs_s[threadIdx.x * 8 + k] = cs[k];
     }
   }
   if (dx_colsum) {
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&dx_colsum[i], cs_s[i]);
+    for (int i = threadIdx.x; i < C; i += 256) {
+      float a = 0.f;
+      for (int l = 0; l < lanes; ++l) a += cs_s[(l * cvs + (i >> 3)) * 8 + (i & 7)];
+      atomicAdd(&dx_colsum[i], a);
+    }
   }
 }
 
@@ -553,7 +608,7 @@ extern "C" int og_gn_stats(const void* x, int N, int64_t V, int C, int G, double
              "gn_stats: need C%%8==0, G<=64, (C/G)%%8==0 (C=%d G=%d)", C, G);
   OG_REQUIRE(C <= 2048, "gn_stats: C=%d > 2048", C);
   long long rpb;
-  const dim3 grid = reduce_grid(N, V, &rpb);
+  const dim3 grid = reduce_grid(N, V, &rpb, 6);
   og_gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), V, C, G, rpb, sums);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -590,8 +645,8 @@ extern "C" int og_affine_act_bwd_reduce(const void* dy, const void* x, const flo
   OG_REQUIRE(dy && x && A && B && S, "affine_act_bwd_reduce: null pointer");
   OG_REQUIRE(C % 8 == 0 && C <= 2048, "affine_act_bwd_reduce: C=%d must be a multiple of 8 and <= 2048", C);
   long long rpb;
-  const dim3 grid = reduce_grid(N, V, &rpb);
-  og_affine_act_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+  const dim3 grid = reduce_grid(N, V, &rpb, 6);
+  og_affine_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, V, C, act, rpb, S);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -656,7 +711,7 @@ extern "C" int og_gn_act_bwd(const void* dy, const void* x, const float* A, cons
   long long rpb;
   const dim3 grid = reduce_grid(N, V, &rpb, 6);
   const double inv_M = 1.0 / ((double)V * (C / G));
-  og_gn_act_bwd_kernel<<<grid, 256, dx_colsum ? C * sizeof(float) : 0, (cudaStream_t)stream>>>(
+  og_gn_act_bwd_kernel<<<grid, 256, dx_colsum ? 256 * 8 * sizeof(float) : 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, S, mean_rstd, gamma, beta, cond_scale,
       reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), dgamma, dbeta, dcond_scale, dcond_shift,
       dx_colsum, V, C, G, inv_M, act, rpb);
