@@ -112,6 +112,60 @@ __global__ void og_pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ x, __n
   }
 }
 
+// Vector form for p*q*r in {2, 4, 8}: one thread owns 8 consecutive output channels of ONE input voxel, i.e. a
+// contiguous run of 8*PQR input channels (PQR 16-byte loads), transposes the 8 x PQR block in registers and
+// writes one 16-byte vector to each of the PQR output voxels. Loads and stores are both fully coalesced; the
+// scalar kernel above gathers 2-byte elements PQR apart and ran ~20x below the HBM roofline.
+template <int PQR>
+__global__ void __launch_bounds__(256)
+    og_pixel_shuffle_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int H, int W, int c, int p,
+                                int q, int r, long long total, int inverse) {
+  const int cv = c >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int oct = (int)(i % cv);
+    long long vin = i / cv;
+    const long long xoff = (vin * cv + oct) * PQR;  // in uint4 units: voxel row has cv*PQR vectors
+    const int w = (int)(vin % W);
+    vin /= W;
+    const int h = (int)(vin % H);
+    vin /= H;
+    const int t = (int)(vin % T);
+    const int n = (int)(vin / T);
+    union Blk {
+      uint4 v[PQR];
+      unsigned short e[8 * PQR];
+    };
+    Blk a, b;
+    if (!inverse) {
+#pragma unroll
+      for (int k = 0; k < PQR; ++k) a.v[k] = __ldg(x + xoff + k);
+#pragma unroll
+      for (int sub = 0; sub < PQR; ++sub)
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) b.e[sub * 8 + cc] = a.e[cc * PQR + sub];
+    }
+#pragma unroll
+    for (int sub = 0; sub < PQR; ++sub) {
+      const int pp = sub / (q * r), qq = (sub / r) % q, rr = sub % r;
+      const long long ov = (((long long)n * T * p + t * p + pp) * (H * q) + h * q + qq) * (long long)(W * r) + w * r + rr;
+      if (!inverse)
+        y[ov * cv + oct] = b.v[sub];
+      else
+        b.v[sub] = __ldg(y + ov * cv + oct);
+    }
+    if (inverse) {
+#pragma unroll
+      for (int sub = 0; sub < PQR; ++sub)
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) a.e[cc * PQR + sub] = b.e[sub * 8 + cc];
+      uint4* xw = const_cast<uint4*>(x);
+#pragma unroll
+      for (int k = 0; k < PQR; ++k) xw[xoff + k] = a.v[k];
+    }
+  }
+}
+
 // im2col: x NDHWC (bf16) -> col [M = N*To*Ho*Wo][kpad], k = tap*C + ci; zero for padding / OOB / k >= ntaps*C
 __global__ void og_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int T, int H,
                                  int W, int C, int To, int Ho, int Wo, int kt, int kh, int kw, int st, int sh, int sw,
@@ -496,8 +550,21 @@ extern "C" int og_pixel_shuffle3d(const void* x, void* y, int inverse, int N, in
   OG_REQUIRE(c % 8 == 0 && p >= 1 && q >= 1 && r >= 1, "pixel_shuffle3d: c=%d must be a multiple of 8", c);
   const long long total = (long long)N * T * p * H * q * W * r * (c / 8);
   // forward: x un-shuffled (read), y shuffled (written). inverse: y shuffled (read), x un-shuffled (written).
-  og_pixel_shuffle_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, T, H, W, c, p, q, r, total, inverse);
+  const int pqr = p * q * r;
+  const long long tv = (long long)N * T * H * W * (c / 8);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (aligned && pqr == 8)
+    og_pixel_shuffle_vec_kernel<8><<<ew_blocks(tv, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, T, H, W, c, p, q, r, tv, inverse);
+  else if (aligned && pqr == 4)
+    og_pixel_shuffle_vec_kernel<4><<<ew_blocks(tv, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, T, H, W, c, p, q, r, tv, inverse);
+  else if (aligned && pqr == 2)
+    og_pixel_shuffle_vec_kernel<2><<<ew_blocks(tv, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, T, H, W, c, p, q, r, tv, inverse);
+  else
+    og_pixel_shuffle_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, T, H, W, c, p, q, r, total, inverse);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;
