@@ -317,8 +317,17 @@ def main():
         peak_tf = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
         roofline = None
         if dom:
+            traffic, traffic_note = None, None
+            try:    # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')))[dom]
+                traffic = tj['traffic_bytes']
+                traffic_note = (f"ncu --set full, one launch of {tj['shape']}: dram read {tj['dram_read_bytes']} + "
+                                f"write {tj['dram_write_bytes']} B; algorithmic {tj['algorithmic_bytes']} B")
+            except Exception:
+                pass
             roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': kern[dom]['tflops'], 'peak': peak_tf,
-                        'unit': 'TFLOP/s', 'frac': kern[dom]['tflops'] / peak_tf, 'traffic': None,
+                        'unit': 'TFLOP/s', 'frac': kern[dom]['tflops'] / peak_tf, 'traffic': traffic,
+                        'traffic_note': traffic_note,
                         'peak_source': peak_src + ' sustained bf16', 'kernels': kern,
                         'conv_flop_per_step': sum(d['flop'] for d in kinds.values()) / prof_steps,
                         'timing': f'CUDA events around each launch over {prof_steps} eagerly launched steps after the '
