@@ -10,7 +10,7 @@
 //   P  = exp(S*scale - m) softmax warps: one TMEM lane (= query row) per thread, online max / sum in registers,
 //                         P written as bf16 into a 128-byte-swizzled smem tile (the A operand of the next MMA)
 //   PV = P V             tcgen05.mma, A = P (K-major, smem), B = V tile (MN-major: keys are the K dim)
-//   O  = O*alpha + PV    in registers (64 fp32 per thread)
+//   O += PV              accumulated in TMEM by the MMA; rescaled in place only when a row maximum jumps (lazy rescale)
 // Q/K/V tiles arrive by 3-D TMA (rows beyond S are zero-filled and masked to -inf).
 // Backward recomputes P from the saved log-sum-exp and accumulates dK/dV in TMEM per key tile, dQ via
 // fp32 reductions (see og_flash_attn_bwd_kernel).
@@ -41,11 +41,15 @@ __device__ __forceinline__ void st_swizzled_chunk(uint8_t* tile, int row, int ch
   *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
 }
 
-__global__ void __launch_bounds__(kFaThreads, 1)
+__global__ void __launch_bounds__(kFaThreads, 2)
     og_flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                              const __grid_constant__ CUtensorMap mapV, const FaParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Two CTAs per SM (their softmax / MMA phases interleave), so every byte counts: 7 tiles + barriers =
+  // 114.8 KB; the 1024-byte alignment the swizzled TMA tiles need is requested from the declaration instead
+  // of reserving slack for a manual round-up (checked below).
+  extern __shared__ __align__(1024) uint8_t smem_fwd[];
+  uint8_t* smem = smem_fwd;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;                         // 16 KiB
   uint8_t* sKV = smem + kTileBytes;           // 2 stages x (K 16 KiB + V 16 KiB)
   uint8_t* sP = sKV + 4 * kTileBytes;         // 2 k-blocks x 16 KiB
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(kFaThreads, 1)
 #pragma unroll
             for (int k = 0; k < kTile / 16; ++k)
               umma_bf16_ss(tPV, umma_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                           umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_pv, k > 0 ? 1u : 0u);
+                           umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_pv, (jj > 0 || k > 0) ? 1u : 0u);
             umma_commit(pv_ready);
             umma_commit(&kv_empty[st]);
           }
@@ -158,31 +162,59 @@ __global__ void __launch_bounds__(kFaThreads, 1)
     __syncwarp();
   } else {
     // ============================ softmax / output warps: thread = query row ============================
+    // Online softmax in base 2 with the scale folded in: p = 2^(s*c - m), c = scale*log2(e)  (one FFMA + one
+    // MUFU.EX2 per element). O stays in TMEM and is accumulated by the PV MMAs; it is only rescaled (TMEM ->
+    // registers -> TMEM) when some row of the warp raised its running maximum by more than 2^8 — until then the
+    // stale maximum is kept, P and l stay mutually consistent and the final O/l is exact (FA-4's lazy rescale).
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
-    float o[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    const float cl2 = p.scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < p.kv_tiles; ++j) {
       mbar_wait(s_ready, j & 1);
       tc_fence_after();
       const int kv_valid = p.S - j * kTile;  // keys of this tile that exist (>= 128 except for the last tile)
-      // pass 1: row max
+      // pass 1: row max of the raw scores
       float mt = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kTile; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_addr + c, v);
         tmem_ld_wait();
+        if (kv_valid >= kTile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) mt = fmaxf(mt, __uint_as_float(v[i]) * p.scale);
+          for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kv_valid) mt = fmaxf(mt, __uint_as_float(v[i]));
+        }
       }
-      const float mn = fmaxf(m, mt);
-      const float alpha = __expf(m - mn);
-      // pass 2: P = exp(s - m), row sum, bf16 P -> swizzled smem
+      mt *= cl2;  // scale > 0
+      float mn = m, alpha = 1.f;
+      if (mt > m + 8.f) {  // (first tile: m = -inf)
+        mn = mt;
+        alpha = ex2_approx(m - mn);
+      }
+      if (j > 0) {
+        // O (TMEM) holds sum_{j' < j} P V once PV_{j-1} has completed
+        mbar_wait(pv_ready, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < kD; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tPV + lane_addr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(tPV + lane_addr + c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: P = 2^(s*c - m), row sum, bf16 P -> swizzled smem
       float ls = 0.f;
 #pragma unroll
       for (int c = 0; c < kTile; c += 32) {
@@ -192,7 +224,8 @@ __global__ void __launch_bounds__(kFaThreads, 1)
         float pf[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          pf[i] = (c + i < kv_valid) ? __expf(__uint_as_float(v[i]) * p.scale - mn) : 0.f;
+          const float e = ex2_approx(fmaf(__uint_as_float(v[i]), cl2, -mn));
+          pf[i] = (kv_valid >= kTile || c + i < kv_valid) ? e : 0.f;
           ls += pf[i];
         }
 #pragma unroll
@@ -208,24 +241,25 @@ __global__ void __launch_bounds__(kFaThreads, 1)
       }
       l = l * alpha + ls;
       m = mn;
-      // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
+      // make the generic-proxy smem writes (and the TMEM rescale) visible to the tensor core, then signal
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      // O = O * alpha + P V
-      mbar_wait(pv_ready, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tPV + lane_addr + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
     }
+    // final O: wait for the last PV, normalise
+    mbar_wait(pv_ready, (p.kv_tiles - 1) & 1);
+    tc_fence_after();
+    float o[kD];
+#pragma unroll
+    for (int c = 0; c < kD; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tPV + lane_addr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c + i] = __uint_as_float(v[i]);
+    }
+    tc_fence_before();
     const int qrow = q0 + row;
     if (qrow < p.S) {
       const float inv = 1.f / l;
@@ -264,7 +298,7 @@ __global__ void __launch_bounds__(kFaThreads, 1)
           *reinterpret_cast<uint4*>(dst2 + i) = u;
         }
       }
-      if (p.lse) p.lse[((long long)seq * p.nh + h) * p.S + qrow] = m + __logf(l);
+      if (p.lse) p.lse[((long long)seq * p.nh + h) * p.S + qrow] = (m + __log2f(l)) * 0.6931471805599453f;
     }
   }
 
@@ -574,6 +608,7 @@ extern "C" int og_flash_attn_fwd(const void* q, const void* k, const void* v, vo
   OG_REQUIRE(q && k && v && out, "flash_attn_fwd: null pointer");
   OG_REQUIRE(n_head >= 1 && C == n_head * kD, "flash_attn_fwd: needs d_head = 64 (C=%d, n_head=%d)", C, n_head);
   OG_REQUIRE(nseq > 0 && S > 0, "flash_attn_fwd: empty problem");
+  OG_REQUIRE(scale > 0.f, "flash_attn_fwd: scale must be positive (the row maximum is taken on raw scores)");
   FaParams p;
   p.S = S; p.C = C; p.nh = n_head; p.nseq = nseq;
   p.q_tiles = (S + kTile - 1) / kTile;
@@ -589,11 +624,13 @@ extern "C" int og_flash_attn_fwd(const void* q, const void* k, const void* v, vo
   if ((r = make_seq_map(&mq, q, nseq, S, C)) != OG_OK) return r;
   if ((r = make_seq_map(&mk, k, nseq, S, C)) != OG_OK) return r;
   if ((r = make_seq_map(&mv, v, nseq, S, C)) != OG_OK) return r;
-  const size_t smem_bytes = 7 * kTileBytes + 1024 + 256;
+  const size_t smem_bytes = 7 * kTileBytes + 128;
   static bool attr = false;
   if (!attr) {
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   const long long grid = (long long)nseq * n_head * p.q_tiles;

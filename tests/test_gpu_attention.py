@@ -54,12 +54,14 @@ def test_rope_layernorm_fwd_bwd(kind, C):
     assert_close(db, br.grad, 2e-3, 2e-3 * br.grad.abs().max().item(), 'dbeta')
 
 
-@pytest.mark.parametrize('S,nh', [(64, 2), (256, 2), (320, 1), (1024, 4)])
-def test_flash_attention_fwd_bwd(S, nh):
+# amp = 2 with 8 heads (scale = 1.0) gives scores of +-100: the running row maximum jumps by far more than the
+# lazy-rescale threshold (2^8) between key tiles, so the in-TMEM rescale of O is exercised, not only the first tile
+@pytest.mark.parametrize('S,nh,amp', [(64, 2, 0.5), (256, 2, 0.5), (320, 1, 0.5), (1024, 4, 0.5), (640, 8, 2.0)])
+def test_flash_attention_fwd_bwd(S, nh, amp):
     nseq, C = 3, 64 * nh
     scale = nh * 64 ** -0.5                                   # the reference's (quirky) scale, attention.py:195
-    q = bf16_round(O.det_uniform(f'fa.q.{S}', (nseq, S, C), 0.5))
-    k = bf16_round(O.det_uniform(f'fa.k.{S}', (nseq, S, C), 0.5))
+    q = bf16_round(O.det_uniform(f'fa.q.{S}', (nseq, S, C), amp))
+    k = bf16_round(O.det_uniform(f'fa.k.{S}', (nseq, S, C), amp))
     v = bf16_round(O.det_uniform(f'fa.v.{S}', (nseq, S, C)))
     do = bf16_round(O.det_uniform(f'fa.do.{S}', (nseq, S, C)))
     qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
