@@ -24,6 +24,7 @@ static constexpr int kD = 64;            // head dim
 static constexpr int kTile = 128;        // queries / keys per tile
 static constexpr int kTileBytes = kTile * kD * 2;  // 16 KiB
 static constexpr int kFaThreads = 192;
+static constexpr int kFaBwdThreads = 320;  // warp 0 TMA, warp 1 MMA, 8 softmax warps (two per TMEM lane quarter)
 
 struct FaParams {
   int S, C, nh, nseq;
@@ -332,7 +333,7 @@ struct FaBwdParams {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kFaThreads, 1)
+__global__ void __launch_bounds__(kFaBwdThreads, 1)
     og_flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                              const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
                              const FaBwdParams p) {
@@ -340,9 +341,11 @@ __global__ void __launch_bounds__(kFaThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sFix = smem;                    // stationary pair: MODE 0: K_j, V_j ; MODE 1: Q_i, dO_i   (2 x 16 KiB)
   uint8_t* sStr = smem + 2 * kTileBytes;   // streamed pair, 2 stages x (2 x 16 KiB)
-  uint8_t* sP = sStr + 4 * kTileBytes;     // P  bf16 [2 k-blocks][128][128 B]
-  uint8_t* sDS = sP + 2 * kTileBytes;      // dS bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * kTileBytes);
+  // P and dS are DOUBLE-buffered: the softmax warps write the tiles of step `it` while the gradient MMAs of step
+  // it-1 (issued after S_it / dP_it, i.e. not covered by sd_ready) are still reading theirs.
+  uint8_t* sP = sStr + 4 * kTileBytes;     // P  bf16 [2 buffers][2 k-blocks][128][128 B]
+  uint8_t* sDS = sP + 4 * kTileBytes;      // dS bf16, same shape
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 4 * kTileBytes);
   uint64_t* fix_full = bars;
   uint64_t* str_full = bars + 1;   // [2]
   uint64_t* str_empty = bars + 3;  // [2]
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(kFaThreads, 1)
       mbar_init(&str_empty[s], 1);
     }
     mbar_init(sd_ready, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(kFaThreads, 1)
       const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0u, 0u);  // S, dP: both operands K-major
       const uint32_t idesc_mm = umma_idesc_bf16(128, 64, 1u, 1u);   // dV, dK: A (P / dS transposed) and B MN-major
       const uint32_t idesc_km = umma_idesc_bf16(128, 64, 0u, 1u);   // dQ: A = dS K-major, B = K MN-major
-      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
       mbar_wait(fix_full, 0);
       for (int it = 0; it <= p.tiles; ++it) {
         if (it < p.tiles) {
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(kFaThreads, 1)
             tc_fence_after();
           }
           const uint32_t fixa = smem_u32(sFix), stra = smem_u32(sStr + st * 2 * kTileBytes);
+          const uint32_t p_addr = p_base + (jj & 1) * 2 * kTileBytes, ds_addr = ds_base + (jj & 1) * 2 * kTileBytes;
           if (!elect_one()) {
           } else if (MODE == 0) {
             const uint32_t q_addr = stra, do_addr = stra + kTileBytes;
@@ -477,31 +481,39 @@ __global__ void __launch_bounds__(kFaThreads, 1)
     }
     __syncwarp();
   } else {
+    // 8 warps: warps w and w+4 share TMEM lane quarter (w & 3) and split the 128 columns of S / dP in halves.
+    // The backward softmax has no cross-column reduction (lse and delta are per-row inputs), so the split is free
+    // and doubles the warps per scheduler. p = 2^(s*c - lse*log2e); dS is written WITHOUT the softmax scale,
+    // which is applied once per output element to the dK / dQ accumulators instead of once per score.
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = qd * 32 + lane;  // TMEM lane: query row of the current pair
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float cl2 = p.scale * 1.4426950408889634f;
     float lse_fix = 0.f, delta_fix = 0.f;
     if (MODE == 1) {
       const int qrow = own * kTile + row;
       if (qrow < p.S) {
-        lse_fix = p.lse[((long long)seq * p.nh + h) * p.S + qrow];
+        lse_fix = p.lse[((long long)seq * p.nh + h) * p.S + qrow] * 1.4426950408889634f;
         delta_fix = p.delta[((long long)seq * p.nh + h) * p.S + qrow];
       }
     }
     for (int it = 0; it < p.tiles; ++it) {
       const int q_tile = MODE == 0 ? it : own, kv_tile = MODE == 0 ? own : it;
       const int qrow = q_tile * kTile + row;
-      float lse = lse_fix, delta = delta_fix;
+      float lse2 = lse_fix, delta = delta_fix;
       if (MODE == 0 && qrow < p.S) {
-        lse = p.lse[((long long)seq * p.nh + h) * p.S + qrow];
+        lse2 = p.lse[((long long)seq * p.nh + h) * p.S + qrow] * 1.4426950408889634f;
         delta = p.delta[((long long)seq * p.nh + h) * p.S + qrow];
       }
       const bool q_ok = qrow < p.S;
       const int kv_valid = p.S - kv_tile * kTile;
+      const bool full = (q_tile + 1) * kTile <= p.S && kv_valid >= kTile;  // warp-uniform fast path
       mbar_wait(sd_ready, it & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < kTile; c += 32) {
+      for (int cc = 0; cc < 64; cc += 32) {
+        const int c = half * 64 + cc;
         uint32_t vs[32], vd[32];
         tmem_ld_32x32(tS + lane_addr + c, vs);
         tmem_ld_32x32(tDP + lane_addr + c, vd);
@@ -509,10 +521,10 @@ __global__ void __launch_bounds__(kFaThreads, 1)
         float pf[32], df[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const bool ok = q_ok && (c + i < kv_valid);
-          const float pv = ok ? __expf(__uint_as_float(vs[i]) * p.scale - lse) : 0.f;
+          float pv = ex2_approx(fmaf(__uint_as_float(vs[i]), cl2, -lse2));
+          if (!full) pv = (q_ok && (c + i < kv_valid)) ? pv : 0.f;
           pf[i] = pv;
-          df[i] = pv * (__uint_as_float(vd[i]) - delta) * p.scale;
+          df[i] = pv * (__uint_as_float(vd[i]) - delta);
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -523,13 +535,13 @@ __global__ void __launch_bounds__(kFaThreads, 1)
             u.y = pack_bf16x2(pf[i + 2], pf[i + 3]);
             u.z = pack_bf16x2(pf[i + 4], pf[i + 5]);
             u.w = pack_bf16x2(pf[i + 6], pf[i + 7]);
-            st_swizzled_chunk(sP + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+            st_swizzled_chunk(sP + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
           }
           u.x = pack_bf16x2(df[i], df[i + 1]);
           u.y = pack_bf16x2(df[i + 2], df[i + 3]);
           u.z = pack_bf16x2(df[i + 4], df[i + 5]);
           u.w = pack_bf16x2(df[i + 6], df[i + 7]);
-          st_swizzled_chunk(sDS + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+          st_swizzled_chunk(sDS + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
         }
       }
       fence_proxy_async_smem();
@@ -537,29 +549,29 @@ __global__ void __launch_bounds__(kFaThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // accumulators complete: TMEM lane = output row (kv row in MODE 0, query row in MODE 1)
+    // accumulators complete: TMEM lane = output row (kv row in MODE 0, query row in MODE 1); the two warps of a
+    // lane quarter take 32 of the 64 columns each. dK / dQ carry the softmax scale here.
     mbar_wait_relaxed(acc_ready, 0);
     tc_fence_after();
     const int orow = own * kTile + row;
     for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
       __nv_bfloat16* base = MODE == 1 ? p.dq : (a == 0 ? p.dv : p.dk);
       const uint32_t tacc = a == 0 ? tAcc0 : tAcc1;
+      const float osc = (MODE == 0 && a == 0) ? 1.f : p.scale;
+      const int c = half * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(tacc + lane_addr + c, v);
+      tmem_ld_wait();
+      if (orow < p.S) {
+        __nv_bfloat16* dst = base + ((long long)seq * p.S + orow) * p.C + h * kD + c;
 #pragma unroll
-      for (int c = 0; c < kD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tacc + lane_addr + c, v);
-        tmem_ld_wait();
-        if (orow < p.S) {
-          __nv_bfloat16* dst = base + ((long long)seq * p.S + orow) * p.C + h * kD + c;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            u.y = pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-            u.z = pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-            u.w = pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-            *reinterpret_cast<uint4*>(dst + i) = u;
-          }
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[i]) * osc, __uint_as_float(v[i + 1]) * osc);
+          u.y = pack_bf16x2(__uint_as_float(v[i + 2]) * osc, __uint_as_float(v[i + 3]) * osc);
+          u.z = pack_bf16x2(__uint_as_float(v[i + 4]) * osc, __uint_as_float(v[i + 5]) * osc);
+          u.w = pack_bf16x2(__uint_as_float(v[i + 6]) * osc, __uint_as_float(v[i + 7]) * osc);
+          *reinterpret_cast<uint4*>(dst + i) = u;
         }
       }
     }
@@ -668,7 +680,7 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
   if ((r = make_seq_map(&mk, k, nseq, S, C)) != OG_OK) return r;
   if ((r = make_seq_map(&mv, v, nseq, S, C)) != OG_OK) return r;
   if ((r = make_seq_map(&mdo, dout, nseq, S, C)) != OG_OK) return r;
-  const size_t smem_bytes = 10 * kTileBytes + 1024 + 256;
+  const size_t smem_bytes = 14 * kTileBytes + 1024 + 256;
   static bool attr = false;
   if (!attr) {
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -678,9 +690,9 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
     attr = true;
   }
   const long long grid = (long long)nseq * n_head * p.tiles;
-  og_flash_attn_bwd_kernel<0><<<(unsigned)grid, kFaThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+  og_flash_attn_bwd_kernel<0><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
   OG_CHECK_CUDA(cudaGetLastError());
-  og_flash_attn_bwd_kernel<1><<<(unsigned)grid, kFaThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+  og_flash_attn_bwd_kernel<1><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(2);
   return OG_OK;
