@@ -194,6 +194,158 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Vector form of the backward pass for C % 256 == 0: lane l owns the 4 consecutive channel pairs
+// [128 j + 4 l, +4) of chunk j (one 16-byte load per tensor and chunk instead of four 4-byte ones) and the
+// per-lane arrays are sized by the template, not by the C <= 1024 maximum: 216 -> ~128 registers, two resident
+// blocks per SM and 4x the bytes in flight. Same arithmetic as the scalar kernel above.
+template <int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
+    og_rope_ln_bwd_vec_kernel(const uint4* __restrict__ x, const float* __restrict__ freq,
+                              const float* __restrict__ gamma, float eps, const uint4* __restrict__ g0,
+                              const uint4* __restrict__ g1, const uint4* __restrict__ g2,
+                              const uint4* __restrict__ add, uint4* __restrict__ dx, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, long long rows, long long pos_div, int pos_mod) {
+  constexpr int NP = 4 * NCH;      // pairs per lane
+  constexpr int C = 256 * NCH;
+  constexpr int VPR = 32 * NCH;    // uint4 vectors per row
+  extern __shared__ float sh[];    // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float fq[NP], gm0[NP], gm1[NP];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int p = 128 * j + 4 * lane + e;
+      fq[4 * j + e] = __ldg(freq + p);
+      gm0[4 * j + e] = __ldg(gamma + 2 * p);
+      gm1[4 * j + e] = __ldg(gamma + 2 * p + 1);
+    }
+  float dg0[NP], dg1[NP], db0[NP], db1[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) dg0[i] = dg1[i] = db0[i] = db1[i] = 0.f;
+  auto unpack = [](const uint4& u, float (&a)[4], float (&b)[4]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __bfloat1622float2(h[e]);
+      a[e] = t.x;
+      b[e] = t.y;
+    }
+  };
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float pos = (float)((row / pos_div) % pos_mod);
+    const long long vb = row * VPR + lane;
+    uint4 ux[NCH], ug[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      ux[j] = __ldg(x + vb + 32 * j);
+      ug[j] = __ldg(g0 + vb + 32 * j);
+    }
+    float r0[NP], r1[NP], sn[NP], cs[NP];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float a[4], b[4];
+      unpack(ux[j], a, b);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        sincosf(pos * fq[i], &sn[i], &cs[i]);
+        r0[i] = a[e] * cs[i] - b[e] * sn[i];
+        r1[i] = b[e] * cs[i] + a[e] * sn[i];
+        s += r0[i] + r1[i];
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      r0[i] -= mean;
+      r1[i] -= mean;
+      ss += r0[i] * r0[i] + r1[i] * r1[i];
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+    float gh0[NP], gh1[NP];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float ga[4], gb[4];
+      unpack(ug[j], ga, gb);
+      if (g1) {
+        float ta[4], tb[4];
+        unpack(__ldg(g1 + vb + 32 * j), ta, tb);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ga[e] += ta[e];
+          gb[e] += tb[e];
+        }
+      }
+      if (g2) {
+        float ta[4], tb[4];
+        unpack(__ldg(g2 + vb + 32 * j), ta, tb);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ga[e] += ta[e];
+          gb[e] += tb[e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        const float xh0 = r0[i] * rstd, xh1 = r1[i] * rstd;
+        db0[i] += ga[e];
+        db1[i] += gb[e];
+        dg0[i] = fmaf(ga[e], xh0, dg0[i]);
+        dg1[i] = fmaf(gb[e], xh1, dg1[i]);
+        gh0[i] = ga[e] * gm0[i];
+        gh1[i] = gb[e] * gm1[i];
+        m1 += gh0[i] + gh1[i];
+        m2 += gh0[i] * xh0 + gh1[i] * xh1;
+        r0[i] = xh0;
+        r1[i] = xh1;
+      }
+    }
+    m1 = warp_sum(m1) / (float)C;
+    m2 = warp_sum(m2) / (float)C;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float aa[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+      if (add) unpack(__ldg(add + vb + 32 * j), aa, ab);
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        const float d0 = rstd * (gh0[i] - m1 - r0[i] * m2);
+        const float d1 = rstd * (gh1[i] - m1 - r1[i] * m2);
+        const float o0 = d0 * cs[i] + d1 * sn[i] + aa[e];   // R^T
+        const float o1 = -d0 * sn[i] + d1 * cs[i] + ab[e];
+        ow[e] = pack_bf16x2(o0, o1);
+      }
+      dx[vb + 32 * j] = o;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int p = 128 * j + 4 * lane + e, i = 4 * j + e;
+      atomicAdd(&sh[2 * p], dg0[i]);
+      atomicAdd(&sh[2 * p + 1], dg1[i]);
+      atomicAdd(&sh[C + 2 * p], db0[i]);
+      atomicAdd(&sh[C + 2 * p + 1], db1[i]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dgamma[i], sh[i]);
+    atomicAdd(&dbeta[i], sh[C + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // temporal attention, one warp per (batch b, pixel p, head h). T <= 32, d = 64 (lane owns 2 dims... no:
 // lane t owns QUERY row t). K/V rows of the sequence sit in shared memory (broadcast reads).
@@ -443,6 +595,25 @@ extern "C" int og_rope_ln_bwd(const void* x, const float* freq, const float* gam
   OG_REQUIRE(x && freq && gamma && g0 && dx && dgamma && dbeta && rows > 0, "rope_ln_bwd: bad arguments");
   OG_REQUIRE(C % 2 == 0 && C <= 2 * 32 * kMaxPairsPerLane, "rope_ln_bwd: C=%d must be even and <= 1024", C);
   int grid = row_grid(rows, 8);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g0) | reinterpret_cast<uintptr_t>(g1) |
+                        reinterpret_cast<uintptr_t>(g2) | reinterpret_cast<uintptr_t>(add) |
+                        reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+  if (vec_ok && (C == 256 || C == 512 || C == 1024)) {
+    if (grid > num_sms() * 4) grid = num_sms() * 4;  // 2 resident blocks per SM, 2 waves; bounds the dgamma/dbeta atomics
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t shb = 2 * C * sizeof(float);
+#define OG_ROPE_BWD(NCH)                                                                                          \
+    og_rope_ln_bwd_vec_kernel<NCH><<<grid, 256, shb, st>>>((const uint4*)x, freq, gamma, eps, (const uint4*)g0,     \
+                                                           (const uint4*)g1, (const uint4*)g2, (const uint4*)add,  \
+                                                           (uint4*)dx, dgamma, dbeta, rows, pos_div, pos_mod)
+    if (C == 256) OG_ROPE_BWD(1);
+    else if (C == 512) OG_ROPE_BWD(2);
+    else OG_ROPE_BWD(4);
+#undef OG_ROPE_BWD
+    OG_CHECK_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return OG_OK;
+  }
   if (grid > num_sms() * 2) grid = num_sms() * 2;  // fewer blocks -> fewer dgamma/dbeta atomics
   og_rope_ln_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat162*)x, freq, gamma, eps, (const __nv_bfloat162*)g0, (const __nv_bfloat162*)g1,
