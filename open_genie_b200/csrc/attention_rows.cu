@@ -352,6 +352,25 @@ __global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
 // q rows: q[((b*T + t)*P + p)*C + h*64 ...]; kv either the same layout (kv_bcast = 0) or [b][t][C]
 // broadcast over pixels (kv_bcast = 1: the latent-action conditioning, attention.py:362-363).
 // ------------------------------------------------------------------------------------------------
+// Work distribution shared by both kernels: tasks are ordered (b, h, pixel) with the PIXEL fastest and every warp
+// owns one contiguous range of them, so consecutive tasks of a warp share (b, h): the broadcast-K/V gradient can
+// then be accumulated in registers across the whole range and flushed with one set of atomics per (b, h) change
+// instead of one per pixel (8192 atomics per address before). When T <= 16 a warp runs TWO tasks at once, one per
+// half-warp (lane = sub * 16 + t), so no lane idles on the short sequences the models use (T = 16).
+struct TaskRange {
+  long long begin, end;
+};
+__device__ __forceinline__ TaskRange warp_task_range(long long ntask, int tpw) {
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  long long per = (ntask + nw - 1) / nw;
+  per = (per + tpw - 1) / tpw * tpw;
+  TaskRange r;
+  r.begin = w * per;
+  r.end = r.begin + per < ntask ? r.begin + per : ntask;
+  return r;
+}
+
 template <int D>
 __global__ void __launch_bounds__(128)
     og_temporal_attn_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
@@ -362,28 +381,34 @@ __global__ void __launch_bounds__(128)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __nv_bfloat16* ks = smem_bf + warp * (2 * 32 * D);
   __nv_bfloat16* vs = ks + 32 * D;
-  const long long task0 = (long long)blockIdx.x * 4 + warp;
+  const int tpad = T <= 16 ? 16 : 32, tpw = 32 / tpad;
+  const int sub = lane / tpad, t = lane % tpad;
   const long long ntask = (long long)B * P * nh;
-  const long long stride = (long long)gridDim.x * 4;
-  for (long long task = task0; task < ntask; task += stride) {
-    const int h = (int)(task % nh);
-    const long long bp = task / nh;
-    const long long p = bp % P;
-    const int b = (int)(bp / P);
+  const TaskRange tr = warp_task_range(ntask, tpw);
+  for (long long base = tr.begin; base < tr.end; base += tpw) {
     __syncwarp();
-    // stage K, V: T rows x D: each row is D*2 bytes contiguous; lanes copy 4-byte words
-    for (int t = 0; t < T; ++t) {
-      const long long kr = kv_bcast ? ((long long)b * T + t) * C + h * D : (((long long)b * T + t) * P + p) * C + h * D;
+    // stage K, V rows of the warp's tpw tasks: smem row = sub * tpad + t, D*2 bytes each (one 4-byte word per lane)
+    for (int r = 0; r < 32; ++r) {
+      const int rs = r / tpad, rt = r % tpad;
+      const long long task = base + rs;
+      if (rt >= T || task >= tr.end) continue;  // warp-uniform
+      const long long pp = task % P, bh = task / P;
+      const int hh = (int)(bh % nh), bb = (int)(bh / nh);
+      const long long kr = kv_bcast ? ((long long)bb * T + rt) * C + hh * D : (((long long)bb * T + rt) * P + pp) * C + hh * D;
       const uint32_t* ksrc = reinterpret_cast<const uint32_t*>(k + kr);
       const uint32_t* vsrc = reinterpret_cast<const uint32_t*>(v + kr);
       for (int w = lane; w < D / 2; w += 32) {
-        reinterpret_cast<uint32_t*>(ks + t * D)[w] = __ldg(ksrc + w);
-        reinterpret_cast<uint32_t*>(vs + t * D)[w] = __ldg(vsrc + w);
+        reinterpret_cast<uint32_t*>(ks + r * D)[w] = __ldg(ksrc + w);
+        reinterpret_cast<uint32_t*>(vs + r * D)[w] = __ldg(vsrc + w);
       }
     }
     __syncwarp();
-    if (lane < T) {
-      const int t = lane;
+    const long long task = base + sub;
+    if (t < T && task < tr.end) {
+      const long long p = task % P, bh = task / P;
+      const int h = (int)(bh % nh), b = (int)(bh / nh);
+      const __nv_bfloat16* kt = ks + sub * tpad * D;
+      const __nv_bfloat16* vt = vs + sub * tpad * D;
       const long long qr = (((long long)b * T + t) * P + p) * C + h * D;
       float qf[D], o[D];
 #pragma unroll
@@ -398,7 +423,7 @@ __global__ void __launch_bounds__(128)
         float sc = 0.f;
 #pragma unroll
         for (int i = 0; i < D; i += 2) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ks + s * D + i));
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kt + s * D + i));
           sc = fmaf(qf[i], f.x, sc);
           sc = fmaf(qf[i + 1], f.y, sc);
         }
@@ -407,7 +432,7 @@ __global__ void __launch_bounds__(128)
         l = l * corr + pw;
 #pragma unroll
         for (int i = 0; i < D; i += 2) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vs + s * D + i));
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vt + s * D + i));
           o[i] = fmaf(pw, f.x, o[i] * corr);
           o[i + 1] = fmaf(pw, f.y, o[i + 1] * corr);
         }
@@ -438,7 +463,7 @@ __global__ void __launch_bounds__(128)
                                 int B, int T, long long P, int C, int nh, float scale, int kv_bcast) {
   extern __shared__ __nv_bfloat16 smem_bf[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per warp: K, V, Q, dO rows (bf16) + P and dS matrices (fp32 [32][33])
+  // per warp: K, V, Q, dO rows (bf16, row = sub * tpad + t) + P and dS matrices (fp32 [32][33], row = sub * tpad + t)
   __nv_bfloat16* ks = smem_bf + warp * (4 * 32 * D);
   __nv_bfloat16* vs = ks + 32 * D;
   __nv_bfloat16* qs = vs + 32 * D;
@@ -446,37 +471,60 @@ __global__ void __launch_bounds__(128)
   float* fbase = reinterpret_cast<float*>(smem_bf + 4 * (4 * 32 * D)) + warp * (2 * 32 * 33);
   float* Pm = fbase;
   float* dS = fbase + 32 * 33;
-  const long long task0 = (long long)blockIdx.x * 4 + warp;
+  const int tpad = T <= 16 ? 16 : 32, tpw = 32 / tpad;
+  const int sub = lane / tpad, t = lane % tpad;
   const long long ntask = (long long)B * P * nh;
-  const long long stride = (long long)gridDim.x * 4;
-  for (long long task = task0; task < ntask; task += stride) {
-    const int h = (int)(task % nh);
-    const long long bp = task / nh;
-    const long long p = bp % P;
-    const int b = (int)(bp / P);
+  const TaskRange tr = warp_task_range(ntask, tpw);
+  // broadcast-K/V gradient accumulators of key row `t`, kept across tasks that share (b, h)
+  float dkv[D], dvv[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) dkv[i] = dvv[i] = 0.f;
+  long long acc_bh = -1;
+  auto flush = [&]() {
+    if (acc_bh >= 0 && t < T) {
+      const int hh = (int)(acc_bh % nh), bb = (int)(acc_bh / nh);
+      const long long kr = ((long long)bb * T + t) * C + hh * D;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        atomicAdd(dk_b + kr + i, dkv[i]);
+        atomicAdd(dv_b + kr + i, dvv[i]);
+        dkv[i] = dvv[i] = 0.f;
+      }
+    }
+  };
+  for (long long base = tr.begin; base < tr.end; base += tpw) {
     __syncwarp();
-    for (int t = 0; t < T; ++t) {
-      const long long qr = (((long long)b * T + t) * P + p) * C + h * D;
-      const long long kr = kv_bcast ? ((long long)b * T + t) * C + h * D : qr;
+    for (int r = 0; r < 32; ++r) {
+      const int rs = r / tpad, rt = r % tpad;
+      const long long task = base + rs;
+      if (rt >= T || task >= tr.end) continue;  // warp-uniform
+      const long long pp = task % P, bh = task / P;
+      const int hh = (int)(bh % nh), bb = (int)(bh / nh);
+      const long long qr = (((long long)bb * T + rt) * P + pp) * C + hh * D;
+      const long long kr = kv_bcast ? ((long long)bb * T + rt) * C + hh * D : qr;
       for (int w = lane; w < D / 2; w += 32) {
-        reinterpret_cast<uint32_t*>(ks + t * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(k + kr) + w);
-        reinterpret_cast<uint32_t*>(vs + t * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(v + kr) + w);
-        reinterpret_cast<uint32_t*>(qs + t * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(q + qr) + w);
-        reinterpret_cast<uint32_t*>(dos + t * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(dout + qr) + w);
+        reinterpret_cast<uint32_t*>(ks + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(k + kr) + w);
+        reinterpret_cast<uint32_t*>(vs + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(v + kr) + w);
+        reinterpret_cast<uint32_t*>(qs + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(q + qr) + w);
+        reinterpret_cast<uint32_t*>(dos + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(dout + qr) + w);
       }
     }
     __syncwarp();
+    const long long task = base + sub;
+    const bool live = t < T && task < tr.end;
+    const long long p = live ? task % P : 0, bh = live ? task / P : 0;
+    const int h = (int)(bh % nh), b = (int)(bh / nh);
+    const int r0 = sub * tpad;  // first smem row of this half-warp's task
     // phase 1: row t: scores, softmax, dP, dS ; dQ
-    if (lane < T) {
-      const int t = lane;
+    if (live) {
       float sc[32];
       float m = -INFINITY;
       for (int s = 0; s <= t; ++s) {
         float a = 0.f;
 #pragma unroll
         for (int i = 0; i < D; i += 2) {
-          const float2 fq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qs + t * D + i));
-          const float2 fk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ks + s * D + i));
+          const float2 fq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qs + (r0 + t) * D + i));
+          const float2 fk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ks + (r0 + s) * D + i));
           a = fmaf(fq.x, fk.x, a);
           a = fmaf(fq.y, fk.y, a);
         }
@@ -497,8 +545,8 @@ __global__ void __launch_bounds__(128)
         float a = 0.f;
 #pragma unroll
         for (int i = 0; i < D; i += 2) {
-          const float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dos + t * D + i));
-          const float2 fv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vs + s * D + i));
+          const float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dos + (r0 + t) * D + i));
+          const float2 fv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vs + (r0 + s) * D + i));
           a = fmaf(fo.x, fv.x, a);
           a = fmaf(fo.y, fv.y, a);
         }
@@ -515,13 +563,13 @@ __global__ void __launch_bounds__(128)
           ds = sc[s] * (dp[s] - delta) * scale;
 #pragma unroll
           for (int i = 0; i < D; i += 2) {
-            const float2 fk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ks + s * D + i));
+            const float2 fk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ks + (r0 + s) * D + i));
             dqv[i] = fmaf(ds, fk.x, dqv[i]);
             dqv[i + 1] = fmaf(ds, fk.y, dqv[i + 1]);
           }
         }
-        Pm[t * 33 + s] = pv;
-        dS[t * 33 + s] = ds;
+        Pm[(r0 + t) * 33 + s] = pv;
+        dS[(r0 + t) * 33 + s] = ds;
       }
       const long long qr = (((long long)b * T + t) * P + p) * C + h * D;
 #pragma unroll
@@ -529,32 +577,30 @@ __global__ void __launch_bounds__(128)
         *reinterpret_cast<__nv_bfloat162*>(dq + qr + i) = __floats2bfloat162_rn(dqv[i], dqv[i + 1]);
     }
     __syncwarp();
-    // phase 2: key row s: dK_s = sum_t dS[t][s] Q_t ; dV_s = sum_t P[t][s] dO_t
-    if (lane < T) {
-      const int s = lane;
-      float dkv[D], dvv[D];
+    // phase 2: key row s (= t of this lane): dK_s = sum_t' dS[t'][s] Q_t' ; dV_s = sum_t' P[t'][s] dO_t'
+    if (kv_bcast && live && bh != acc_bh) {
+      flush();
+      acc_bh = bh;
+    }
+    if (live) {
+      const int s = t;
+      if (!kv_bcast) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) dkv[i] = dvv[i] = 0.f;
-      for (int t = s; t < T; ++t) {
-        const float ds = dS[t * 33 + s], pv = Pm[t * 33 + s];
+        for (int i = 0; i < D; ++i) dkv[i] = dvv[i] = 0.f;
+      }
+      for (int tt = s; tt < T; ++tt) {
+        const float ds = dS[(r0 + tt) * 33 + s], pv = Pm[(r0 + tt) * 33 + s];
 #pragma unroll
         for (int i = 0; i < D; i += 2) {
-          const float2 fq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qs + t * D + i));
-          const float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dos + t * D + i));
+          const float2 fq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qs + (r0 + tt) * D + i));
+          const float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dos + (r0 + tt) * D + i));
           dkv[i] = fmaf(ds, fq.x, dkv[i]);
           dkv[i + 1] = fmaf(ds, fq.y, dkv[i + 1]);
           dvv[i] = fmaf(pv, fo.x, dvv[i]);
           dvv[i + 1] = fmaf(pv, fo.y, dvv[i + 1]);
         }
       }
-      if (kv_bcast) {
-        const long long kr = ((long long)b * T + s) * C + h * D;
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          atomicAdd(dk_b + kr + i, dkv[i]);
-          atomicAdd(dv_b + kr + i, dvv[i]);
-        }
-      } else {
+      if (!kv_bcast) {
         const long long kr = (((long long)b * T + s) * P + p) * C + h * D;
 #pragma unroll
         for (int i = 0; i < D; i += 2) {
@@ -564,6 +610,7 @@ __global__ void __launch_bounds__(128)
       }
     }
   }
+  if (kv_bcast) flush();
 }
 
 static int row_grid(long long rows, int warps_per_block) {
