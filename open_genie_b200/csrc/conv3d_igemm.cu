@@ -62,6 +62,7 @@ struct IgemmParams {
   const float* red_B;
   float* red_S;                // ... S[n][c] += (sum dpre, sum dpre*x), dpre = d * act'(x*A+B)   (og_affine_act_bwd_reduce)
   int red_act;
+  int swap;        // operand swap (see below): D^T[cout][256 voxels] = W . X^T, used when Cout tiles are 128 wide
   int splits;      // split-K factor (1 = none): each work item covers a k-block range and reduces into `ws`
   float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zeroed by the launcher) when splits > 1
 };
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================================== MMA issuer =====================================
     {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, (uint32_t)p.block_n, 0u, (uint32_t)p.b_mn_major);
+      const uint32_t idesc_swap = umma_idesc_bf16(kBlockM, 256u, (uint32_t)p.b_mn_major, 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -231,7 +233,23 @@ __global__ void __launch_bounds__(kThreads, 1)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + a_bytes;
-          if (elect_one()) {
+          if (p.swap) {
+            // Swapped operands: A = the 128 x 64 weight tile (M = output channels), B = the TWO voxel sub-tiles as one
+            // 256-row K-major operand (they sit back to back in the stage). One 128x256x16 MMA replaces two
+            // 128x128x16 ones: the same bytes per stage, but 96 instead of 128 B/clk of shared-memory operand reads,
+            // which is what capped the Cout = 128 layers at ~78 % of the Cout = 256 rate.
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t wdesc = p.b_mn_major ? umma_smem_desc_sw128(b_addr + k * 2048, 64 * 128, 1024)
+                                                    : umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                const uint64_t xdesc = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                umma_bf16_ss(d_tmem, wdesc, xdesc, idesc_swap, (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+          } else if (elect_one()) {
             for (int ms = 0; ms < p.m_sub; ++ms) {
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           }
-          __syncwarp();
+          if (!p.swap) __syncwarp();
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -278,7 +296,54 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int n_tile = tile - m_super * p.num_n_tiles;
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      for (int ms = 0; ms < p.m_sub; ++ms) {
+      if (p.swap) {
+        // accumulator is D^T: TMEM lane = output channel (this thread owns channel `co`), column = voxel of the
+        // 256-voxel super tile. 32-voxel chunks are transposed through a [32 voxels][128 channels] bf16 staging tile
+        // shared by the four epilogue warps (double-buffered, one named barrier per chunk), then stored as full
+        // 256-byte voxel rows. Host guarantees: whole boxes, n_out % 128 == 0, no residual / split-K.
+        const TileCoord tcs0 = decode_m_tile(p, m_super * 2), tcs1 = decode_m_tile(p, m_super * 2 + 1);
+        const int co = n_tile * 128 + row;
+        float bsum = 0.f;
+        if (p.bias0) bsum += __ldg(p.bias0 + co);
+        if (p.bias1) bsum += __ldg(p.bias1 + co);
+        const uint32_t t_addr = tmem_base + acc * kAccStride + ((uint32_t)(q * 32) << 16);
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+        float st_s = 0.f, st_ss = 0.f;
+        for (int c = 0; c < 256; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + c, v);
+          tmem_ld_wait();
+          uint8_t* buf = stage_s + ((c >> 5) & 1) * 8192;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(__uint_as_float(v[j]) + bsum);
+            if (p.gn_sums) {
+              const float r = __bfloat162float(hb);
+              st_s += r;
+              st_ss = fmaf(r, r, st_ss);
+            }
+            *reinterpret_cast<__nv_bfloat16*>(buf + j * 256 + row * 2) = hb;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = (warp - 2) * 8 + i * 2 + (lane >> 4);
+            const int vv = c + j;
+            const TileCoord tc = (vv >> 7) ? tcs1 : tcs0;
+            const int r = vv & 127;
+            const int dw = r & ((1 << p.bw_log2) - 1);
+            const int dh = (r >> p.bw_log2) & ((1 << p.bh_log2) - 1);
+            const int dt = (r >> (p.bw_log2 + p.bh_log2)) & ((1 << p.bt_log2) - 1);
+            const int dn = r >> (p.bw_log2 + p.bh_log2 + p.bt_log2);
+            const long long vox = (((long long)(tc.n0 + dn) * p.T + tc.t0 + dt) * p.H + tc.h0 + dh) * p.W + tc.w0 + dw;
+            const uint4 u = *reinterpret_cast<const uint4*>(buf + j * 256 + (lane & 15) * 16);
+            *reinterpret_cast<uint4*>(outp + vox * p.ldo + n_tile * 128 + (lane & 15) * 8) = u;
+          }
+        }
+        fl_s += st_s;
+        fl_ss += st_ss;
+      }
+      for (int ms = 0; ms < (p.swap ? 0 : p.m_sub); ++ms) {
       const TileCoord tc = decode_m_tile(p, m_super * p.m_sub + ms);
       const int dw = row & ((1 << p.bw_log2) - 1);
       const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
@@ -714,6 +779,13 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   if (!attr_set) {
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  // operand swap for 128-wide Cout tiles (two voxel sub-tiles form the N = 256 operand): whole boxes only
+  p.swap = (p.block_n == 128 && p.m_sub == 2 && p.fast_store && p.splits == 1 && !residual && !red_S &&
+            n_out % 128 == 0 && (p.num_m_tiles % 2 == 0) && W % bw == 0 && H % bh == 0 && T % bt == 0 && N % bn == 0)
+               ? 1 : 0;
+  if (const char* e = getenv("OG_IGEMM_SWAP")) {
+    if (atoi(e) == 0) p.swap = 0;
   }
   // fused epilogue reductions need: staged bf16 stores, no split-K, every CTA tile inside one sample
   const int tiles_per_sample = p.tiles_w * p.tiles_h * p.tiles_t;

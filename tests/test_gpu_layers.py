@@ -259,3 +259,37 @@ def test_mse_loss_and_layout_roundtrip():
     # layout round trip is exact for bf16-representable data
     x = bf16_round(O.det_uniform('rt.x', (2, 18, 4, 8, 8)))
     assert torch.equal(ops.to_reference(ops.to_internal(x.to(DEV))).cpu(), x)
+
+
+def test_operand_swapped_gemm_matches_plain_tiles(monkeypatch):
+    """Cout = 128 layers with >= 2 x #SM voxel tiles run the operand-swapped GEMM (D^T = W . X^T, transposing
+    epilogue). At the full tokenizer size (8 x 16 x 64 x 64, C = 128) its output, fused GroupNorm statistics and
+    data gradient must equal those of the plain 128 x 128 tile path (OG_IGEMM_SWAP=0): same k order, same fp32
+    accumulation, so bit-exact bf16 — and a small corner is checked against the fp32 oracle."""
+    import torch.nn.functional as F
+    from open_genie_b200.module.video import CausalConv3d
+    from open_genie_b200 import ops
+    torch.manual_seed(0)
+    m = CausalConv3d(128, 128, 3).to(DEV)
+    x = torch.randn(8, 128, 16, 64, 64, device=DEV)
+    xi = ops.to_internal(x, torch.bfloat16)
+
+    def run():
+        xin = xi.detach().clone().requires_grad_(True)
+        y = m(xin)
+        g = torch.sin(torch.arange(y.numel(), device=DEV, dtype=torch.float32)).view_as(y).to(y.dtype)
+        y.backward(g)
+        return y.detach().float(), xin.grad.detach().float()
+
+    y1, dx1 = run()
+    monkeypatch.setenv('OG_IGEMM_SWAP', '0')
+    y0, dx0 = run()
+    assert torch.equal(y1, y0), (y1 - y0).abs().max().item()
+    assert torch.equal(dx1, dx0), (dx1 - dx0).abs().max().item()
+    # corner of sample 0 against the oracle (causal front pad in time, symmetric in space)
+    w = bf16_round(m.conv3d.weight.detach().float().cpu())
+    b = m.conv3d.bias.detach().float().cpu()
+    xc = bf16_round(ops.to_reference(xi[:1, :, :4, :10, :10].float()).cpu())
+    yo = O.causal_conv3d(xc, w, b)[:, :, :, :8, :8]
+    got = ops.to_reference(y1[:1, :, :4, :8, :8]).cpu()
+    assert_close(got, bf16_round(yo), BF16_ULP, BF16_ULP * yo.abs().max().item(), 'swapped GEMM corner vs oracle')
