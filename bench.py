@@ -232,13 +232,13 @@ def main():
         return float(t.item())
 
     # ---------------- warm-up (>= 3 steps) + capture of the whole step into one CUDA graph ----------------
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = (not args.no_graph) and world == 1   # N>1: eager launches (capturing the NCCL buckets hung in testing)
     for _ in range(max(args.warmup, 3)):
         eager_step(dev_video)
     barrier()
     if use_graph:
         from open_genie_b200.graph import GraphedTrainStep
-        train_step = GraphedTrainStep(model, opt, dev_video, warmup=1)
+        train_step = GraphedTrainStep(model, opt, dev_video, warmup=1, reducer=reducer)
         for _ in range(2):
             train_step(dev_video)
     else:
