@@ -204,6 +204,7 @@ def main():
     n_params = sum(p.numel() for p in model.parameters())
     opt = model.configure_optimizers()                      # FusedAdamW, AdamW defaults
     reducer = GradBucketAllReducer(model.parameters()) if world > 1 else None
+    og.enable_zero_arena(True)   # every step below ends with zero_grad(set_to_none=True): the arena contract holds
     B = args.batch
     torch.manual_seed(1234 + rank)
     host_video = torch.randn(B, 3, FRAMES, RES, RES).pin_memory()

@@ -24,6 +24,72 @@ def _stream() -> int:
 
 
 _WS = {}
+# ------------------------------------------------------------------------------------------------
+# step-scoped zero arena
+# ------------------------------------------------------------------------------------------------
+class _ZeroArena:
+    """Bump allocator for the zero-initialised accumulators of one training step (weight-gradient buffers the
+    wgrad kernel reduces into, bias / gamma / beta gradients, GroupNorm sums): ONE fill of the extent used by the
+    previous step replaces ~540 small fill launches per tokenizer step.
+
+    Contract (why it is opt-in — `enable_zero_arena()`; `GraphedTrainStep` turns it on): everything handed out
+    is valid until the first allocation after the next `mark_step()` (called by `FusedAdamW.step()`), so
+    gradients must be released with `zero_grad(set_to_none=True)` every step and must not be kept across steps.
+    Loss values are never placed here."""
+
+    def __init__(self):
+        self.enabled = False
+        self.buf = {}        # device -> uint8 tensor
+        self.off = {}        # device -> bytes handed out this step
+        self.want = {}       # device -> bytes requested this step (including what did not fit)
+        self.dirty = {}      # device -> a step boundary passed since the last allocation
+
+    def mark_step(self):
+        for d in self.dirty:
+            self.dirty[d] = True
+
+    def _begin(self, dev):
+        used, want = self.off.get(dev, 0), self.want.get(dev, 0)
+        buf = self.buf.get(dev)
+        capturing = dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()
+        if (buf is None or want > buf.numel()) and want > 0 and not capturing:
+            buf = torch.zeros(int(want * 1.05) + 65536, dtype=torch.uint8, device=dev)   # grown: all zero already
+            self.buf[dev] = buf
+        elif buf is not None and used > 0:
+            buf[:used].zero_()
+        self.off[dev], self.want[dev], self.dirty[dev] = 0, 0, False
+
+    def zeros(self, shape, dtype, device):
+        if not self.enabled:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        dev = torch.device(device)
+        if self.dirty.setdefault(dev, True):
+            self._begin(dev)
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        al = (nbytes + 255) & ~255
+        self.want[dev] = self.want.get(dev, 0) + al
+        buf, off = self.buf.get(dev), self.off.get(dev, 0)
+        if buf is None or off + al > buf.numel() or nbytes == 0:
+            return torch.zeros(shape, dtype=dtype, device=device)
+        self.off[dev] = off + al
+        return buf[off:off + nbytes].view(dtype).view(shape)
+
+
+ZERO_ARENA = _ZeroArena()
+
+
+def enable_zero_arena(on: bool = True):
+    """Opt in to the step-scoped zero arena (see _ZeroArena for the lifetime contract)."""
+    ZERO_ARENA.enabled = bool(on)
+
+
+def _zeros(shape, dtype, device):
+    return ZERO_ARENA.zeros(shape, dtype, device)
+
+
 # tuning switches (environment): fuse GroupNorm statistics / backward reductions into the GEMM epilogues
 import os as _os
 FUSE_STATS = _os.environ.get('OG_FUSE_STATS', '1') != '0'
@@ -244,7 +310,7 @@ class _Conv3dFn(torch.autograd.Function):
         def wgrad(xin, cin, kt, kh, kw, pt, ph, pw, shape5, dims):
             """fp32 gradient with the parameter's channels_last_3d memory: [cout][tap][cin]."""
             rows = cpad if cpad != cout else cout
-            g = torch.zeros((rows, kt * kh * kw * cin), dtype=f32, device=dev)
+            g = _zeros((rows, kt * kh * kw * cin), f32, dev)
             _conv_call('wgrad', 2.0 * dims[0] * dims[1] * dims[2] * dims[3] * cout * min(cin, geom.k_main) * kt * kh * kw,
                        'og_conv3d_wgrad', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(), g.shape[1],
                       kt, kh, kw, pt, ph, pw, dims[0], dims[1], dims[2], dims[3], s)
@@ -285,7 +351,7 @@ class _Conv3dFn(torch.autograd.Function):
                 g = wgrad(col, geom.kpad, 1, 1, 1, 0, 0, 0, ctx.w_shapes[0], (1, 1, 1, B * To * Ho * Wo))
                 dw = g[:, :geom.k_main].reshape(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
         if (ctx.has_bias[0] and need[2]) or (ctx.has_bias[1] and need[5]):
-            dbs = torch.zeros(cout, dtype=f32, device=dev)
+            dbs = _zeros(cout, f32, dev)
             _lib.call('og_colsum', dyb.data_ptr(), B * To * Ho * Wo, cout, cpad, dbs.data_ptr(), s)
             if ctx.has_bias[0] and need[2]:
                 db = dbs
@@ -312,7 +378,7 @@ class _GroupNormActFn(torch.autograd.Function):
         V = T * H * W
         s = _stream()
         dev = xi.device
-        sums = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+        sums = _zeros((B, G, 2), torch.float64, dev)
         _lib.call('og_gn_stats', xi.data_ptr(), B, V, C, G, sums.data_ptr(), s)
         A = torch.empty((B, C), dtype=f32, device=dev)
         Bc = torch.empty((B, C), dtype=f32, device=dev)
@@ -340,11 +406,11 @@ class _GroupNormActFn(torch.autograd.Function):
         s = _stream()
         dev = xi.device
         dyb = _as_bf16_rows(dy, C, C)
-        S = torch.zeros((B, C, 2), dtype=f32, device=dev)
+        S = _zeros((B, C, 2), f32, dev)
         _lib.call('og_affine_act_bwd_reduce', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), act,
                   S.data_ptr(), B, V, C, s)
-        dgamma = torch.zeros(C, dtype=f32, device=dev) if gamma is not None else None
-        dbeta = torch.zeros(C, dtype=f32, device=dev) if beta is not None else None
+        dgamma = _zeros(C, f32, dev) if gamma is not None else None
+        dbeta = _zeros(C, f32, dev) if beta is not None else None
         dcs = torch.empty((B, C), dtype=f32, device=dev) if has_cs else None
         dcsh = torch.empty((B, C), dtype=f32, device=dev) if has_csh else None
         dx = None
@@ -587,8 +653,8 @@ class _SpaceAttnFn(torch.autograd.Function):
                    o.data_ptr(), dy.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(),
                    dv.data_ptr(), B * T, S, C, n_head, scale, s)
         dx = torch.empty_like(x)
-        dgamma = torch.zeros(C, dtype=f32, device=x.device)
-        dbeta = torch.zeros(C, dtype=f32, device=x.device)
+        dgamma = _zeros(C, f32, x.device)
+        dbeta = _zeros(C, f32, x.device)
         _lib.call('og_rope_ln_bwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), eps, dq.data_ptr(), dk.data_ptr(),
                   dv.data_ptr(), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, C, 1, S, s)
         return dx, None, dgamma, dbeta, None, None, None
@@ -632,8 +698,8 @@ class _TimeAttnFn(torch.autograd.Function):
         dq = torch.empty_like(x)
         dkc = dvc = None
         if bcast:
-            dkc = torch.zeros((B, T, C), dtype=f32, device=x.device)
-            dvc = torch.zeros((B, T, C), dtype=f32, device=x.device)
+            dkc = _zeros((B, T, C), f32, x.device)
+            dvc = _zeros((B, T, C), f32, x.device)
             _lib.call('og_temporal_attn_bwd', q.data_ptr(), kc.data_ptr(), vc.data_ptr(), dy.data_ptr(), dq.data_ptr(),
                       None, None, dkc.data_ptr(), dvc.data_ptr(), B, T, P, C, n_head, scale, 1, s)
             g1 = g2 = None
@@ -643,8 +709,8 @@ class _TimeAttnFn(torch.autograd.Function):
                       dk.data_ptr(), dv.data_ptr(), None, None, B, T, P, C, n_head, scale, 0, s)
             g1, g2 = dk, dv
         dx = torch.empty_like(x)
-        dgamma = torch.zeros(C, dtype=f32, device=x.device)
-        dbeta = torch.zeros(C, dtype=f32, device=x.device)
+        dgamma = _zeros(C, f32, x.device)
+        dbeta = _zeros(C, f32, x.device)
         _lib.call('og_rope_ln_bwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), eps, dq.data_ptr(), _ptr(g1),
                   _ptr(g2), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), B * T * P, C, P, T, s)
         return dx, None, dgamma, dbeta, dkc, dvc, None, None, None
@@ -662,7 +728,7 @@ class _FfnFn(torch.autograd.Function):
         V = T * H * W
         s = _stream()
         dev = x.device
-        sums = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+        sums = _zeros((B, G, 2), torch.float64, dev)
         _lib.call('og_gn_stats', x.data_ptr(), B, V, C, G, sums.data_ptr(), s)
         A = torch.empty((B, C), dtype=f32, device=dev)
         Bc = torch.empty((B, C), dtype=f32, device=dev)
@@ -690,17 +756,17 @@ class _FfnFn(torch.autograd.Function):
         dy = _rows_bf16(dy)
         ws = _workspace(dev, B * V * C * 4)
         dh = torch.empty_like(x)
-        S = torch.zeros((B, C, 2), dtype=f32, device=dev)
+        S = _zeros((B, C, 2), f32, dev)
         # data gradient with the GroupNorm backward reduction fused into its epilogue
         _conv_call('dgrad', 2.0 * B * V * C * geom.k_main, 'og_conv3d_dgrad', dy.data_ptr(), C, C, packed.data_ptr(),
                    packed.shape[1], 0, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, dh.data_ptr(), 0, B, T, H,
                    W, C, ws.data_ptr(), ws.numel(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), 0, S.data_ptr(), s)
-        g = torch.zeros((C, geom.ntaps * C), dtype=f32, device=dev)
+        g = _zeros((C, geom.ntaps * C), f32, dev)
         _conv_call('wgrad', 2.0 * B * V * C * geom.k_main, 'og_conv3d_wgrad', dy.data_ptr(), C, hn.data_ptr(), C,
                    g.data_ptr(), g.shape[1], geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, B, T, H, W, s)
         dw = g.view(C, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
-        dgw = torch.zeros(C, dtype=f32, device=dev)
-        dgb = torch.zeros(C, dtype=f32, device=dev)
+        dgw = _zeros(C, f32, dev)
+        dgb = _zeros(C, f32, dev)
         dx = torch.empty_like(x)
         _lib.call('og_gn_act_bwd', dh.data_ptr(), x.data_ptr(), A.data_ptr(), Bc.data_ptr(), S.data_ptr(), mr.data_ptr(),
                   gn_w.data_ptr(), gn_b.data_ptr(), None, G, 0, dy.data_ptr(), dx.data_ptr(), dgw.data_ptr(),
@@ -756,8 +822,8 @@ class _EmbedAddFn(torch.autograd.Function):
         tok, act = ctx.saved_tensors
         ts, as_, hw = ctx.shapes
         dy = _rows_bf16(dy)
-        dtw = torch.zeros(ts, dtype=f32, device=dy.device)
-        daw = torch.zeros(as_, dtype=f32, device=dy.device)
+        dtw = _zeros(ts, f32, dy.device)
+        daw = _zeros(as_, f32, dy.device)
         _lib.call('og_embed_add_bwd', tok.data_ptr(), act.data_ptr(), dy.data_ptr(), dtw.data_ptr(), daw.data_ptr(),
                   tok.numel(), hw, ts[1], ts[0], as_[0], _stream())
         return None, None, dtw, daw
@@ -818,7 +884,7 @@ class _ResBlockFn(torch.autograd.Function):
         s = _stream()
         dev = xi.device
         if x_sums is None:
-            x_sums = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+            x_sums = _zeros((B, G, 2), torch.float64, dev)
             _lib.call('og_gn_stats', xi.data_ptr(), B, V, C0, G, x_sums.data_ptr(), s)
         coef = torch.empty((2, 2, B, max(C0, C1)), dtype=f32, device=dev)       # A1,B1 / A2,B2
         mr = torch.empty((2, B, G, 2), dtype=f32, device=dev)
@@ -830,7 +896,7 @@ class _ResBlockFn(torch.autograd.Function):
                   a1.data_ptr(), A1.data_ptr(), B1.data_ptr(), mr[0].data_ptr(), B, V, C0, s)
         ws = _workspace(dev, B * V * C1 * 4)
         fuse_stats = G == 1 and FUSE_STATS
-        sums2 = torch.zeros((B, G, 2), dtype=torch.float64, device=dev)
+        sums2 = _zeros((B, G, 2), torch.float64, dev)
         h1 = empty_internal(B, C1, T, H, W, bf16, dev)
         _conv_call('fwd', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_fwd', a1.data_ptr(), C0, geom1.kt, geom1.kh,
                    geom1.kw, geom1.pt, geom1.ph, geom1.pw, None, 0, packed1.data_ptr(), packed1.shape[1], _ptr(b1), None,
@@ -842,7 +908,7 @@ class _ResBlockFn(torch.autograd.Function):
         _lib.call('og_gn_act_fwd', h1.data_ptr(), sums2.data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, None, eps, G, 1,
                   a2.data_ptr(), A2.data_ptr(), B2.data_ptr(), mr[1].data_ptr(), B, V, C1, s)
         y = empty_internal(B, C1, T, H, W, bf16, dev)
-        y_sums = torch.zeros((B, 1, 2), dtype=torch.float64, device=dev)
+        y_sums = _zeros((B, 1, 2), torch.float64, dev)
         _conv_call('fwd', 2.0 * B * V * C1 * (geom2.k_main + C0), 'og_conv3d_fwd', a2.data_ptr(), C1, geom2.kt, geom2.kh,
                    geom2.kw, geom2.pt, geom2.ph, geom2.pw, xi.data_ptr(), C0, packed2.data_ptr(), packed2.shape[1],
                    _ptr(b2), _ptr(bres), None, y.data_ptr(), 0, B, T, H, W, C1, ws.data_ptr(), ws.numel(),
@@ -868,18 +934,18 @@ class _ResBlockFn(torch.autograd.Function):
         ld2 = packed2.shape[1]
 
         def wgrad(dyt, cout, xin, cin, g):
-            gr = torch.zeros((cout, g.ntaps * cin), dtype=f32, device=dev)
+            gr = _zeros((cout, g.ntaps * cin), f32, dev)
             _conv_call('wgrad', 2.0 * B * V * cout * cin * g.ntaps, 'og_conv3d_wgrad', dyt.data_ptr(), cout,
                        xin.data_ptr(), cin, gr.data_ptr(), gr.shape[1], g.kt, g.kh, g.kw, g.pt, g.ph, g.pw, B, T, H, W, s)
             return gr.view(cout, g.kt, g.kh, g.kw, cin).permute(0, 4, 1, 2, 3)
 
         gone = ConvGeom(C0, C1, (1, 1, 1))
-        db2 = torch.zeros(C1, dtype=f32, device=dev)
+        db2 = _zeros(C1, f32, dev)
         _lib.call('og_colsum', dyb.data_ptr(), B * V, C1, C1, db2.data_ptr(), s)
         dw2 = wgrad(dyb, C1, a2, C1, geom2)
         dwres = wgrad(dyb, C1, xi, C0, gone)
         # conv2 data gradient + fused GN2 backward reduction
-        S2 = torch.zeros((B, C1, 2), dtype=f32, device=dev)
+        S2 = _zeros((B, C1, 2), f32, dev)
         d_a2 = empty_internal(B, C1, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * geom2.k_main, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(),
                    ld2, 0, geom2.kt, geom2.kh, geom2.kw, geom2.pt, geom2.ph, geom2.pw, d_a2.data_ptr(), 0, B, T, H, W, C1,
@@ -888,7 +954,7 @@ class _ResBlockFn(torch.autograd.Function):
         if not FUSE_RED:
             _lib.call('og_affine_act_bwd_reduce', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1,
                       S2.data_ptr(), B, V, C1, s)
-        small = torch.zeros((3, C1), dtype=f32, device=dev)              # dgamma2, dbeta2, db1 in one fill
+        small = _zeros((3, C1), f32, dev)              # dgamma2, dbeta2, db1 in one fill
         dg2w, dg2b, db1 = small[0], small[1], small[2]
         d_h1 = empty_internal(B, C1, T, H, W, bf16, dev)
         _lib.call('og_gn_act_bwd', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), S2.data_ptr(),
@@ -896,9 +962,9 @@ class _ResBlockFn(torch.autograd.Function):
                   dg2b.data_ptr(), None, None, db1.data_ptr() if has_b1 else None, B, V, C1, s)
         dw1 = wgrad(d_h1, C1, a1, C0, geom1)
         dx = None
-        dg1w, dg1b = torch.zeros(C0, dtype=f32, device=dev), torch.zeros(C0, dtype=f32, device=dev)
+        dg1w, dg1b = _zeros(C0, f32, dev), _zeros(C0, f32, dev)
         # conv1 data gradient + fused GN1 backward reduction; shortcut data gradient; GN1 backward apply adds both
-        S1 = torch.zeros((B, C0, 2), dtype=f32, device=dev)
+        S1 = _zeros((B, C0, 2), f32, dev)
         d_a1 = empty_internal(B, C0, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_dgrad', d_h1.data_ptr(), C1, C1,
                    packed1.data_ptr(), packed1.shape[1], 0, geom1.kt, geom1.kh, geom1.kw, geom1.pt, geom1.ph, geom1.pw,

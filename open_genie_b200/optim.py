@@ -74,6 +74,8 @@ class FusedAdamW(Optimizer):
             by_group.setdefault(id(e[4]), []).append(e)
         for ents in by_group.values():
             self._launch(ents)
+        from . import ops
+        ops.ZERO_ARENA.mark_step()          # gradients consumed: the step-scoped zero arena may be recycled
         return loss
 
     def _launch(self, ents):

@@ -79,3 +79,26 @@ def test_shard_batch_partitions_clips():
         assert spans[0][0] == 0 and spans[-1][1] == 32
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     assert [shard_batch(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def test_zero_arena_lifetime_contract():
+    """ops._ZeroArena: first step only measures, later steps hand out zeroed views of one buffer; a view is
+    recycled (and re-zeroed) by the first allocation after mark_step()."""
+    import torch
+    from open_genie_b200 import ops
+    a = ops._ZeroArena()
+    assert a.zeros((2, 3), torch.float32, 'cpu').data_ptr() != 0          # disabled: plain torch.zeros
+    a.enabled = True
+    x = a.zeros((3, 4), torch.float32, 'cpu')                               # step 1: nothing to carve from yet
+    assert a.buf.get(torch.device('cpu')) is None and x.sum() == 0
+    a.mark_step()
+    y = a.zeros((3, 4), torch.float32, 'cpu')
+    z = a.zeros((5,), torch.float64, 'cpu')
+    assert y.untyped_storage().data_ptr() == z.untyped_storage().data_ptr()  # one buffer
+    y += 1
+    z += 2
+    big = a.zeros((1 << 20,), torch.float32, 'cpu')                          # does not fit: falls back, grows next step
+    assert big.untyped_storage().data_ptr() != y.untyped_storage().data_ptr()
+    a.mark_step()
+    w = a.zeros((3, 4), torch.float32, 'cpu')
+    assert w.sum() == 0 and a.buf[torch.device('cpu')].numel() >= 4 << 20
