@@ -77,6 +77,75 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Vector form of the forward pass for C % 256 == 0 (same lane -> channel mapping as the vector backward below:
+// lane l owns the 4 consecutive pairs [128 j + 4 l, +4) of chunk j, i.e. one 16-byte load / store per chunk).
+template <int NCH>
+__global__ void __launch_bounds__(256)
+    og_rope_ln_fwd_vec_kernel(const uint4* __restrict__ x, const float* __restrict__ freq,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                              uint4* __restrict__ y, long long rows, long long pos_div, int pos_mod) {
+  constexpr int NP = 4 * NCH;
+  constexpr int C = 256 * NCH;
+  constexpr int VPR = 32 * NCH;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float fq[NP], gm0[NP], gm1[NP], bt0[NP], bt1[NP];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int p = 128 * j + 4 * lane + e;
+      fq[4 * j + e] = __ldg(freq + p);
+      gm0[4 * j + e] = __ldg(gamma + 2 * p);
+      gm1[4 * j + e] = __ldg(gamma + 2 * p + 1);
+      bt0[4 * j + e] = __ldg(beta + 2 * p);
+      bt1[4 * j + e] = __ldg(beta + 2 * p + 1);
+    }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float pos = (float)((row / pos_div) % pos_mod);
+    const long long vb = row * VPR + lane;
+    uint4 ux[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) ux[j] = __ldg(x + vb + 32 * j);
+    float r0[NP], r1[NP];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&ux[j]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        const float2 v = __bfloat1622float2(h[e]);
+        float sn, cs;
+        sincosf(pos * fq[i], &sn, &cs);
+        r0[i] = v.x * cs - v.y * sn;
+        r1[i] = v.y * cs + v.x * sn;
+        s += r0[i] + r1[i];
+      }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float a = r0[i] - mean, b = r1[i] - mean;
+      ss += a * a + b * b;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        ow[e] = pack_bf16x2((r0[i] - mean) * rstd * gm0[i] + bt0[i], (r1[i] - mean) * rstd * gm1[i] + bt1[i]);
+      }
+      y[vb + 32 * j] = o;
+    }
+  }
+}
+
 // backward: g = g0 (+ g1 + g2) ; dx = R^T LN'(g) (+ add). dgamma / dbeta accumulated per lane over the
 // warp's rows, then shared + global atomics once per block.
 __global__ void __launch_bounds__(256)
@@ -388,18 +457,20 @@ __global__ void __launch_bounds__(128)
   for (long long base = tr.begin; base < tr.end; base += tpw) {
     __syncwarp();
     // stage K, V rows of the warp's tpw tasks: smem row = sub * tpad + t, D*2 bytes each (one 4-byte word per lane)
-    for (int r = 0; r < 32; ++r) {
-      const int rs = r / tpad, rt = r % tpad;
+    for (int rs = 0; rs < tpw; ++rs) {
       const long long task = base + rs;
-      if (rt >= T || task >= tr.end) continue;  // warp-uniform
-      const long long pp = task % P, bh = task / P;
+      if (task >= tr.end) break;  // warp-uniform
+      const long long pp = task % P, bh = task / P;  // decoded once per task, not per row
       const int hh = (int)(bh % nh), bb = (int)(bh / nh);
-      const long long kr = kv_bcast ? ((long long)bb * T + rt) * C + hh * D : (((long long)bb * T + rt) * P + pp) * C + hh * D;
-      const uint32_t* ksrc = reinterpret_cast<const uint32_t*>(k + kr);
-      const uint32_t* vsrc = reinterpret_cast<const uint32_t*>(v + kr);
-      for (int w = lane; w < D / 2; w += 32) {
-        reinterpret_cast<uint32_t*>(ks + r * D)[w] = __ldg(ksrc + w);
-        reinterpret_cast<uint32_t*>(vs + r * D)[w] = __ldg(vsrc + w);
+      for (int rt = 0; rt < T; ++rt) {
+        const int r = rs * tpad + rt;
+        const long long kr = kv_bcast ? ((long long)bb * T + rt) * C + hh * D : (((long long)bb * T + rt) * P + pp) * C + hh * D;
+        const uint32_t* ksrc = reinterpret_cast<const uint32_t*>(k + kr);
+        const uint32_t* vsrc = reinterpret_cast<const uint32_t*>(v + kr);
+        for (int w = lane; w < D / 2; w += 32) {
+          reinterpret_cast<uint32_t*>(ks + r * D)[w] = __ldg(ksrc + w);
+          reinterpret_cast<uint32_t*>(vs + r * D)[w] = __ldg(vsrc + w);
+        }
       }
     }
     __syncwarp();
@@ -494,19 +565,21 @@ __global__ void __launch_bounds__(128)
   };
   for (long long base = tr.begin; base < tr.end; base += tpw) {
     __syncwarp();
-    for (int r = 0; r < 32; ++r) {
-      const int rs = r / tpad, rt = r % tpad;
+    for (int rs = 0; rs < tpw; ++rs) {
       const long long task = base + rs;
-      if (rt >= T || task >= tr.end) continue;  // warp-uniform
-      const long long pp = task % P, bh = task / P;
+      if (task >= tr.end) break;  // warp-uniform
+      const long long pp = task % P, bh = task / P;  // decoded once per task, not per row
       const int hh = (int)(bh % nh), bb = (int)(bh / nh);
-      const long long qr = (((long long)bb * T + rt) * P + pp) * C + hh * D;
-      const long long kr = kv_bcast ? ((long long)bb * T + rt) * C + hh * D : qr;
-      for (int w = lane; w < D / 2; w += 32) {
-        reinterpret_cast<uint32_t*>(ks + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(k + kr) + w);
-        reinterpret_cast<uint32_t*>(vs + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(v + kr) + w);
-        reinterpret_cast<uint32_t*>(qs + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(q + qr) + w);
-        reinterpret_cast<uint32_t*>(dos + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(dout + qr) + w);
+      for (int rt = 0; rt < T; ++rt) {
+        const int r = rs * tpad + rt;
+        const long long qr = (((long long)bb * T + rt) * P + pp) * C + hh * D;
+        const long long kr = kv_bcast ? ((long long)bb * T + rt) * C + hh * D : qr;
+        for (int w = lane; w < D / 2; w += 32) {
+          reinterpret_cast<uint32_t*>(ks + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(k + kr) + w);
+          reinterpret_cast<uint32_t*>(vs + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(v + kr) + w);
+          reinterpret_cast<uint32_t*>(qs + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(q + qr) + w);
+          reinterpret_cast<uint32_t*>(dos + r * D)[w] = __ldg(reinterpret_cast<const uint32_t*>(dout + qr) + w);
+        }
       }
     }
     __syncwarp();
@@ -629,6 +702,20 @@ extern "C" int og_rope_ln_fwd(const void* x, const float* freq, const float* gam
                               void* y, int64_t rows, int C, int64_t pos_div, int pos_mod, og_stream_t stream) {
   OG_REQUIRE(x && freq && gamma && beta && y && rows > 0, "rope_ln_fwd: bad arguments");
   OG_REQUIRE(C % 2 == 0 && C <= 2 * 32 * kMaxPairsPerLane, "rope_ln_fwd: C=%d must be even and <= 1024", C);
+  if ((C == 256 || C == 512 || C == 1024) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = row_grid(rows, 8);
+    if (C == 256)
+      og_rope_ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod);
+    else if (C == 512)
+      og_rope_ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod);
+    else
+      og_rope_ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod);
+    OG_CHECK_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return OG_OK;
+  }
   og_rope_ln_fwd_kernel<<<row_grid(rows, 8), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat162*)x, freq, gamma, beta, eps, (__nv_bfloat162*)y, rows, C, pos_div, pos_mod);
   OG_CHECK_CUDA(cudaGetLastError());
