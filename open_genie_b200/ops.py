@@ -53,7 +53,8 @@ class _ZeroArena:
         buf = self.buf.get(dev)
         capturing = dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()
         if (buf is None or want > buf.numel()) and want > 0 and not capturing:
-            buf = torch.zeros(int(want * 1.05) + 65536, dtype=torch.uint8, device=dev)   # grown: all zero already
+            # (capped: a long run of forward-only calls between two optimizer steps must not balloon the arena)
+            buf = torch.zeros(min(int(want * 1.05) + 65536, 16 << 30), dtype=torch.uint8, device=dev)   # fresh: already zero
             self.buf[dev] = buf
         elif buf is not None and used > 0:
             buf[:used].zero_()
