@@ -3,11 +3,14 @@
 // These are HBM-bound passes (2+2 bytes per element), so the design is about traffic:
 //   * statistics: ONE read of x  -> per-(sample, group) sum / sum-of-squares (fp32 partials, fp64 combine)
 //   * apply     : one read + one write; the whole GN / AdaGN / affine / SiLU chain is folded into a
-//                 per-(sample, channel) scale A and shift B computed by a tiny finalize kernel:
+//                 per-(sample, channel) scale A and shift B:
 //                     y = act(x * A[n][c] + B[n][c])
 //                 A = rstd * gamma * s,  B = (beta - mean * rstd * gamma) * s + a        (s, a: AdaGN)
-//   * backward  : one reduce pass (dy, x) -> per-(n,c) sums, tiny finalize, one apply pass
+//                 (og_gn_act_fwd derives A, B inside the apply launch; og_gn_finalize + og_affine_act_fwd are
+//                 the two-launch form kept for (C/G) % 8 != 0)
+//   * backward  : one reduce pass (dy, x) -> per-(n,c) sums, then one apply pass
 //                     dx = P[n][c] * dpre + Q[n][c] * x + R[n][c]  (+ add)
+//                 whose prologue turns the sums into P, Q, R and the parameter gradients (og_gn_act_bwd)
 //
 // Replaces F.group_norm / nn.GroupNorm + nn.SiLU (genie/module/video.py:607-608,622-623, blueprint
 // 'group_norm'+'silu' tokenizer.py:75-79,163-167), AdaptiveGroupNorm.forward (genie/module/norm.py:55-69)

@@ -887,9 +887,7 @@ class _ResBlockFn(torch.autograd.Function):
         if x_sums is None:
             x_sums = _zeros((B, G, 2), torch.float64, dev)
             _lib.call('og_gn_stats', xi.data_ptr(), B, V, C0, G, x_sums.data_ptr(), s)
-        coef = torch.empty((2, 2, B, max(C0, C1)), dtype=f32, device=dev)       # A1,B1 / A2,B2
         mr = torch.empty((2, B, G, 2), dtype=f32, device=dev)
-        A1, B1, A2, B2 = coef[0, 0, :, :C0], coef[0, 1, :, :C0], coef[1, 0, :, :C1], coef[1, 1, :, :C1]
         A1, B1 = torch.empty((B, C0), dtype=f32, device=dev), torch.empty((B, C0), dtype=f32, device=dev)
         A2, B2 = torch.empty((B, C1), dtype=f32, device=dev), torch.empty((B, C1), dtype=f32, device=dev)
         a1 = empty_internal(B, C0, T, H, W, bf16, dev)
