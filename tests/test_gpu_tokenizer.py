@@ -181,8 +181,10 @@ def test_graphed_train_step_replays_a_real_update():
             with torch.no_grad():
                 expect = float(tok.training_step(video, 0))
             got = step(video).item()
-            assert abs(got - expect) <= 1e-4 * abs(expect), (got, expect, seen)
+            # same kernels on the same parameters; only the order of fp32 atomics (split-K, loss sums) differs
+            assert abs(got - expect) <= 5e-3 * abs(expect), (got, expect, seen)
             seen.append(got)
-        assert len({round(v, 6) for v in seen}) == 3, seen          # three different losses: parameters moved
+        # parameters moved between replays: successive losses differ by far more than that noise
+        assert all(abs(a - b) > 1e-2 * abs(a) for a, b in zip(seen, seen[1:])), seen
     finally:
         ops.enable_zero_arena(False)
