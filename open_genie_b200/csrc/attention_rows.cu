@@ -10,6 +10,8 @@
 // Spatial sequences run over (h w) of one frame, temporal ones over t of one pixel. In NDHWC memory both
 // are ROW-WISE operations on the same [B*T*H*W][C] matrix — only the position index of a row differs —
 // so no 'b c t h w -> (b h w) t c' transposition copy is ever made (the reference makes two per block).
+#include <stdlib.h>
+
 #include "og_host.cuh"
 #include "og_ptx.cuh"
 
@@ -686,6 +688,17 @@ __global__ void __launch_bounds__(128)
   if (kv_bcast) flush();
 }
 
+// experimental mma.sync path (temporal_attn_mma.cu): only with OG_TEMPORAL_MMA=1, d_head = 64, T <= 16
+int launch_temporal_fwd_mma(const void* q, const void* k, const void* v, const void* residual, void* out, int B, int T,
+                            long long P, int C, int n_head, float scale, int kv_bcast, cudaStream_t stream);
+int launch_temporal_bwd_mma(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
+                            float* dk_b, float* dv_b, int B, int T, long long P, int C, int n_head, float scale,
+                            int kv_bcast, cudaStream_t stream);
+static bool temporal_mma_enabled(int D, int T, int C) {
+  const char* e = getenv("OG_TEMPORAL_MMA");
+  return e && atoi(e) == 1 && D == 64 && T <= 16 && C % 8 == 0;
+}
+
 static int row_grid(long long rows, int warps_per_block) {
   long long g = (rows + warps_per_block - 1) / warps_per_block;
   long long cap = (long long)num_sms() * 8;
@@ -765,6 +778,8 @@ extern "C" int og_temporal_attn_fwd(const void* q, const void* k, const void* v,
   OG_REQUIRE(T >= 1 && T <= 32, "temporal_attn_fwd: T=%d must be in [1,32]", T);
   OG_REQUIRE(n_head >= 1 && C % n_head == 0, "temporal_attn_fwd: C=%d not divisible by n_head=%d", C, n_head);
   const int D = C / n_head;
+  if (temporal_mma_enabled(D, T, C))
+    return launch_temporal_fwd_mma(q, k, v, residual, out, B, T, P, C, n_head, scale, kv_bcast, (cudaStream_t)stream);
   const long long ntask = (long long)B * P * n_head;
   long long grid = (ntask + 3) / 4;
   if (grid > (long long)num_sms() * 16) grid = (long long)num_sms() * 16;
@@ -794,6 +809,9 @@ extern "C" int og_temporal_attn_bwd(const void* q, const void* k, const void* v,
   OG_REQUIRE(T >= 1 && T <= 32, "temporal_attn_bwd: T=%d must be in [1,32]", T);
   OG_REQUIRE(n_head >= 1 && C % n_head == 0, "temporal_attn_bwd: C=%d not divisible by n_head=%d", C, n_head);
   const int D = C / n_head;
+  if (temporal_mma_enabled(D, T, C))
+    return launch_temporal_bwd_mma(q, k, v, dout, dq, dk, dv, dk_bcast, dv_bcast, B, T, P, C, n_head, scale, kv_bcast,
+                                   (cudaStream_t)stream);
   const long long ntask = (long long)B * P * n_head;
   long long grid = (ntask + 3) / 4;
   if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
