@@ -2,7 +2,7 @@
 """bench.py — VideoTokenizer train-step frames/sec @ 16x64x64 (BASELINE.json's metric, configs[1]).
 
     python bench.py --gpus N --steps K --warmup W                 # our arm (one process per GPU via torchrun for N>1)
-    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference itself on the host CPU (baseline/_ref), rank 0 only
 
 A "step" is one full training step of the MAGVIT2 VideoTokenizer (GAN / perceptual terms disabled — the
 only configuration in which the reference runs offline) on one synthetic batch of
@@ -91,44 +91,83 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU leg: the reference's algorithm (oracle port) on the host cores.  Test infrastructure used as a
-# measured baseline only — never on the product path.
+# CPU leg: the reference's OWN implementation (the unmodified myscience/open-genie package vendored by
+# __graft_entry__.build() into baseline/_ref, imported through the `lightning` stand-in of oracle/_shim) on the
+# host cores; if that copy is absent, the oracle port of the same algorithm (oracle/genie_oracle.py). A measured
+# baseline only — never on the product path.
 # --------------------------------------------------------------------------------------------------
-def pick_cpu_threads():
-    """MKLDNN conv3d on a big box is often FASTER with fewer threads than os.cpu_count() (cgroup quotas,
-    oversubscription): time one representative conv at a few thread counts (~1 s each) and keep the best."""
-    import torch.nn.functional as F
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def usable_cores():
     try:
-        avail = len(os.sched_getaffinity(0))
+        return len(os.sched_getaffinity(0))
     except Exception:
-        avail = os.cpu_count() or 1
+        return os.cpu_count() or 1
+
+
+def pick_cpu_threads():
+    """Thread policy of the CPU arm, stated in the JSON line: the thread count (powers of two up to the usable cores,
+    plus the usable core count itself) that runs a conv3d forward+backward probe fastest — best of 3 repetitions each,
+    every candidate's time recorded. On a shared 128-core host all 128 threads are an order of magnitude SLOWER than 32
+    (oversubscription), so `os.cpu_count()` threads would flatter the GPU/CPU ratio; the fastest setting is the fair one."""
+    import torch.nn.functional as F
+    avail = usable_cores()
     cands = sorted({c for c in (4, 8, 16, 32, 64, 128, avail) if c <= avail})
-    x = torch.randn(1, 128, 8, 64, 64)
-    w = torch.randn(128, 128, 3, 3, 3)
-    best, best_t = cands[0], float('inf')
+    x = torch.randn(1, 128, 8, 64, 64, requires_grad=True)
+    w = torch.randn(128, 128, 3, 3, 3, requires_grad=True)
+    probe = {}
     for c in cands:
         torch.set_num_threads(c)
-        F.conv3d(x, w, padding=1)
-        t0 = time.perf_counter()
-        F.conv3d(x, w, padding=1)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    torch.set_num_threads(best)
-    return best, avail
+        F.conv3d(x, w, padding=1).sum().backward()
+        best = float('inf')
+        for _ in range(3):
+            t0 = time.perf_counter()
+            F.conv3d(x, w, padding=1).sum().backward()
+            best = min(best, time.perf_counter() - t0)
+        probe[c] = round(best * 1e3, 1)
+    pick = min(probe, key=probe.get)
+    torch.set_num_threads(pick)
+    return pick, avail, probe
 
 
 def cpu_train_step_factory(batch, seed=0):
+    """One MAGVIT2 VideoTokenizer training step (fwd + bwd + AdamW, fp32) on `batch` clips. Returns (step, kind)."""
+    torch.manual_seed(seed)
+    video = torch.randn(batch, 3, FRAMES, RES, RES)
+    if os.path.isdir(os.path.join(REF_DIR, 'genie')):
+        for pth in (os.path.join(ROOT, 'oracle', '_shim'), REF_DIR):
+            if pth not in sys.path:
+                sys.path.insert(0, pth)
+        import copy
+        import torch.nn as nn
+        from genie.tokenizer import MAGVIT2_DEC_DESC, MAGVIT2_ENC_DESC, VideoTokenizer   # the reference itself
+
+        class ZeroLoss(nn.Module):          # GAN / perceptual terms off (VGG weights need a download): SURVEY.md §8c
+            def forward(self, *a, **k):
+                return torch.zeros(())
+
+        model = VideoTokenizer(copy.deepcopy(MAGVIT2_ENC_DESC), copy.deepcopy(MAGVIT2_DEC_DESC), d_codebook=18,
+                               gan_loss_weight=0, perc_loss_weight=0)
+        model.gan_crit = model.perc_crit = ZeroLoss()
+        model.train()
+        opt = model.configure_optimizers()                  # the reference's default: torch.optim.AdamW
+
+        def step():
+            loss = model.training_step(video, 0)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return float(loss.detach())
+        return step, 'reference'
     from oracle import genie_oracle as O
     import open_genie_b200 as og
-    torch.manual_seed(seed)
     model = og.VideoTokenizer(og.MAGVIT2_ENC_DESC, og.MAGVIT2_DEC_DESC, d_codebook=18, gan_loss_weight=0,
                               perc_loss_weight=0)          # CPU construction only: parameter shapes + default init
     sd = {k: v.detach().clone().contiguous().requires_grad_(v.dtype.is_floating_point)
           for k, v in model.state_dict().items()}
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.AdamW(params)                         # the reference's default (genie/tokenizer.py:250)
-    video = torch.randn(batch, 3, FRAMES, RES, RES)
     del model
 
     def step():
@@ -137,16 +176,34 @@ def cpu_train_step_factory(batch, seed=0):
         opt.step()
         opt.zero_grad(set_to_none=True)
         return float(loss.detach())
-    return step
+    return step, 'port'
+
+
+WORKLOAD = ('BASELINE configs[1]: MAGVIT2_ENC/DEC VideoTokenizer training step (fwd + bwd + AdamW), d_codebook=18, '
+            f'{FRAMES}x{RES}x{RES} synthetic video, GAN+perceptual terms off (the reference runs offline only that way)')
+
+
+def cpu_sample_text(batch, threads, avail, kind):
+    what = ('unmodified reference package (baseline/_ref) through its own VideoTokenizer.training_step + AdamW'
+            if kind == 'reference' else 'oracle/genie_oracle.py port of the reference (pinned to reference outputs)')
+    return (f'{batch} clip(s) x {FRAMES} frames per step, fp32 torch CPU, {threads} threads (fastest on a conv3d probe among '
+            f'the {avail} usable cores); {what}')
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads, avail = pick_cpu_threads()
+    threads, avail, probe = pick_cpu_threads()
     batch = args.cpu_batch
-    step = cpu_train_step_factory(batch)
-    for _ in range(args.warmup):
+    step, kind = cpu_train_step_factory(batch)
+    t0 = time.perf_counter()
+    step()                                                  # first (untimed) step doubles as the time probe
+    first = time.perf_counter() - t0
+    if batch > 1 and first * (args.steps + args.warmup) > args.cpu_budget_s:
+        batch = 1                                           # keep the whole run within a few minutes
+        step, kind = cpu_train_step_factory(batch)
+        step()
+    for _ in range(max(args.warmup - 1, 0)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -157,12 +214,9 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'videotokenizer_train_step_frames_per_sec', 'value': fps, 'unit': 'frames/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'MAGVIT2 VideoTokenizer train step (fwd+bwd+AdamW), {FRAMES}x{RES}x{RES} video, '
-                               f'CPU sample of {batch} clip(s) per step'},
-        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{batch} clip(s) x {FRAMES} frames per step, fp32, torch CPU ({threads} threads, '
-                                   f'fastest of the {avail} available); '
-                                   'oracle/genie_oracle.py restatement of the reference (pinned to reference outputs)'},
+        'config': {'workload': WORKLOAD, 'cpu_sample_clips_per_step': batch},
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': threads, 'cores_usable': avail, 'kind': kind,
+                         'thread_probe_ms': probe, 'sample': cpu_sample_text(batch, threads, avail, kind)},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -170,6 +224,32 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------------
+# algorithmic HBM bytes of one launch of the bandwidth-bound kernels, from the C-ABI arguments (DESIGN.md §3:
+# bf16 activations = 2 B/element; what each pass must read + write at minimum)
+def _hbm_bytes(name, a):
+    if name in ('og_gn_stats',):
+        return 2.0 * a['N'] * a['V'] * a['C']
+    if name in ('og_gn_act_fwd', 'og_affine_act_fwd'):
+        return 4.0 * a['N'] * a['V'] * a['C']
+    if name == 'og_affine_act_bwd_reduce':
+        return 4.0 * a['N'] * a['V'] * a['C']
+    if name in ('og_gn_act_bwd', 'og_affine_act_bwd_apply'):
+        return (6.0 + (2.0 if a.get('add') else 0.0)) * a['N'] * a['V'] * a['C']
+    if name == 'og_pixel_shuffle3d':
+        return 4.0 * a['N'] * a['T'] * a['H'] * a['W'] * a['c'] * a['p'] * a['q'] * a['r']
+    if name == 'og_colsum':
+        return 2.0 * a['rows'] * a['C']
+    if name == 'og_rope_ln_fwd':
+        return 4.0 * a['rows'] * a['C']
+    if name == 'og_ncdhw_f32_to_ndhwc':
+        return (4.0 + (4.0 if a['y_f32'] else 2.0)) * a['N'] * a['C'] * a['V']
+    if name in ('og_mse_fwd',):
+        return 8.0 * a['N'] * a['C'] * a['V']
+    if name == 'og_mse_bwd':
+        return (8.0 * a['C'] + 2.0 * a['cpad']) * a['N'] * a['V']
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -177,7 +257,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='clips per GPU (BASELINE configs[1]: 8)')
-    ap.add_argument('--cpu-batch', type=int, default=1, help='clips per CPU-baseline step')
+    ap.add_argument('--cpu-batch', type=int, default=2, help='clips per CPU-baseline step (BASELINE.md §3: B = 2)')
+    ap.add_argument('--cpu-budget-s', type=float, default=300.0,
+                    help='--impl reference: drop to 1 clip per step if (steps+warmup) x first-step time exceeds this')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying the captured step')
     args = ap.parse_args()
@@ -196,15 +278,16 @@ def main():
 
     import open_genie_b200 as og
     from open_genie_b200 import _lib, ops
-    from open_genie_b200.ddp import GradBucketAllReducer
+    from open_genie_b200.ddp import ArenaGradAllReducer
 
     torch.manual_seed(0)
     model = og.VideoTokenizer(og.MAGVIT2_ENC_DESC, og.MAGVIT2_DEC_DESC, d_codebook=18, gan_loss_weight=0,
                               perc_loss_weight=0).to(dev)
     n_params = sum(p.numel() for p in model.parameters())
     opt = model.configure_optimizers()                      # FusedAdamW, AdamW defaults
-    reducer = GradBucketAllReducer(model.parameters()) if world > 1 else None
     og.enable_zero_arena(True)   # every step below ends with zero_grad(set_to_none=True): the arena contract holds
+    # N > 1: ONE gradient exchange per step, all-reduced in place on the step's zero arena (no bucket copies)
+    reducer = ArenaGradAllReducer(model.parameters()) if world > 1 else None
     B = args.batch
     torch.manual_seed(1234 + rank)
     host_video = torch.randn(B, 3, FRAMES, RES, RES).pin_memory()
@@ -233,56 +316,74 @@ def main():
         return float(t.item())
 
     # ---------------- warm-up (>= 3 steps) + capture of the whole step into one CUDA graph ----------------
-    use_graph = (not args.no_graph) and world == 1   # N>1: eager launches (capturing the NCCL buckets hung in testing)
     for _ in range(max(args.warmup, 3)):
         eager_step(dev_video)
     barrier()
+    use_graph = not args.no_graph
+    graph_note = None
     if use_graph:
         from open_genie_b200.graph import GraphedTrainStep
-        train_step = GraphedTrainStep(model, opt, dev_video, warmup=1, reducer=reducer)
+        ok = torch.ones(1, device=dev)
+        try:
+            train_step = GraphedTrainStep(model, opt, dev_video, warmup=3, reducer=reducer)
+        except Exception as e:                              # every rank must take the same path
+            graph_note = f'{type(e).__name__}: {e}'[:200]
+            ok.zero_()
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            use_graph = False
+            if reducer is not None:
+                reducer.bind_arena(None)
+            model.zero_grad(set_to_none=True)
+    if use_graph:
         for _ in range(2):
             train_step(dev_video)
     else:
         train_step = eager_step
     barrier()
 
-    # ---------------- device-resident leg (value) ----------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        train_step(dev_video)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
 
-    # ---------------- end-to-end leg: host batch in, loss out, every step ----------------
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
+    def e2e_step():
         if use_graph:
             loss = train_step(host_video)                  # H2D from pinned memory into the static input + replay
         else:
             loss = train_step(host_video.to(dev, non_blocking=True))
         _ = loss.item()                                    # D2H read of the step's result
-    f1.record()
-    barrier()
-    ms_e2e = max_over_ranks(f0.elapsed_time(f1))
 
-    # ---------------- per-kernel timing pass (eager, CUDA events around every tensor-core launch) ----------
+    # ---------------- timed legs: e2e (a) -> device-resident `value` -> e2e (b) ----------------
+    # The e2e leg brackets the value leg on both sides so that slow clock drift under the power cap cancels in the
+    # comparison of the two (round 1 ran them back to back and e2e came out 1 % FASTER than value).
+    ms_e2e_a = timed(e2e_step)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms_total = timed(lambda: train_step(dev_video))
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e_b = timed(e2e_step)
+    ms_e2e = 0.5 * (ms_e2e_a + ms_e2e_b)
+
+    # ---------------- per-kernel timing pass (eager, CUDA events around every launch of the library) ----------
     # A replayed graph cannot carry timing events, so the roofline numbers come from the same step launched
     # eagerly right after the timed region (same process, same inputs, same kernels and grid sizes).
-    if use_graph:
-        model.zero_grad(set_to_none=True)
+    model.zero_grad(set_to_none=True)
+    if reducer is not None:
+        reducer.bind_arena(None)
     prof_steps = min(args.steps, 3)
+    eager_step(dev_video)                                   # re-sizes the default scope's arena after the graph's private one
     ops.PROFILE = []
+    _lib.TIMING = []
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eager_launch0 = _lib.launch_count()
     p0.record()
@@ -293,6 +394,7 @@ def main():
     ms_prof = p0.elapsed_time(p1)
     launches_per_step = (_lib.launch_count() - eager_launch0) / prof_steps
     prof, ops.PROFILE = ops.PROFILE, None
+    timing, _lib.TIMING = _lib.TIMING, None
     if use_graph:
         launches = int(round(launches_per_step * args.steps))   # kernels executed by the replays of the timed region
 
@@ -309,13 +411,38 @@ def main():
             d['ms'] += a.elapsed_time(b)
             d['flop'] += flops
             d['launches'] += 1
+        peak_tf = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+        peak_bw = peaks.get('hbm_gbs')
         kern = {}
         for k, d in kinds.items():
-            kern[k] = {'launches_per_step': d['launches'] / prof_steps, 'ms_per_step': d['ms'] / prof_steps,
-                       'tflops': d['flop'] / max(d['ms'], 1e-9) * 1e-9,
-                       'share_of_step': (d['ms'] / prof_steps) / max(ms_step, 1e-9)}
-        dom = max(kern, key=lambda k: kern[k]['ms_per_step']) if kern else None
-        peak_tf = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+            tf = d['flop'] / max(d['ms'], 1e-9) * 1e-9
+            kern[k] = {'bound': 'tensor', 'launches_per_step': d['launches'] / prof_steps, 'ms_per_step': d['ms'] / prof_steps,
+                       'tflops': tf, 'frac': tf / peak_tf, 'share_of_step': (d['ms'] / prof_steps) / max(ms_step, 1e-9)}
+        # HBM-bound passes: algorithmic bytes (from the C-ABI arguments) / event time, against the measured copy bandwidth
+        hb = {}
+        for name, cargs, a, b in timing:
+            if name.startswith('og_conv3d'):
+                continue
+            named = dict(zip(_lib.PROTOTYPES[name][2], cargs))
+            d = hb.setdefault(name, {'ms': 0.0, 'bytes': 0.0, 'launches': 0, 'known': True})
+            d['ms'] += a.elapsed_time(b)
+            d['launches'] += 1
+            nb = _hbm_bytes(name, named)
+            if nb is None:
+                d['known'] = False
+            else:
+                d['bytes'] += nb
+        if 'og_adamw_step' in hb:        # 4 fp32 reads (p, g, m, v) + 3 fp32 writes + the bf16 operand copy of conv weights
+            hb['og_adamw_step']['bytes'] = 30.0 * n_params * prof_steps
+            hb['og_adamw_step']['known'] = True
+        for name, d in hb.items():
+            e = {'bound': 'hbm', 'launches_per_step': d['launches'] / prof_steps, 'ms_per_step': d['ms'] / prof_steps,
+                 'share_of_step': (d['ms'] / prof_steps) / max(ms_step, 1e-9)}
+            if d['known'] and d['bytes'] > 0:
+                gbs = d['bytes'] / max(d['ms'], 1e-9) * 1e-6
+                e.update(gbs=gbs, frac=gbs / peak_bw)
+            kern[name] = e
+        dom = max(kinds, key=lambda k: kern[k]['ms_per_step']) if kinds else None
         roofline = None
         if dom:
             traffic, traffic_note = None, None
@@ -326,40 +453,47 @@ def main():
                                 f"write {tj['dram_write_bytes']} B; algorithmic {tj['algorithmic_bytes']} B")
             except Exception:
                 pass
+            conv_flop = sum(d['flop'] for d in kinds.values()) / prof_steps
             roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': kern[dom]['tflops'], 'peak': peak_tf,
                         'unit': 'TFLOP/s', 'frac': kern[dom]['tflops'] / peak_tf, 'traffic': traffic,
                         'traffic_note': traffic_note,
-                        'peak_source': peak_src + ' sustained bf16', 'kernels': kern,
-                        'conv_flop_per_step': sum(d['flop'] for d in kinds.values()) / prof_steps,
+                        'peak_source': peak_src + ' sustained bf16; HBM-bound kernels against hbm_gbs', 'kernels': kern,
+                        'conv_flop_per_step': conv_flop,
+                        'whole_step': {'tflops': conv_flop / (ms_step * 1e-3) * 1e-12,
+                                       'frac': conv_flop / (ms_step * 1e-3) * 1e-12 / peak_tf},
                         'timing': f'CUDA events around each launch over {prof_steps} eagerly launched steps after the '
                                   f'timed region ({ms_prof / prof_steps:.1f} ms/step eager)'}
+        launch = 'whole step (fwd + bwd + NCCL all-reduce + AdamW) replayed as one CUDA graph' if use_graph else \
+            'eager launches' + (f' (graph capture failed: {graph_note})' if graph_note else '')
         line = {
             'metric': 'videotokenizer_train_step_frames_per_sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE configs[1]: MAGVIT2_ENC/DEC VideoTokenizer training step '
-                                   '(fwd + bwd + AdamW, bf16 compute / fp32 master weights), d_codebook=18, '
-                                   'GAN+perceptual terms off (reference runs offline only that way)',
+            'config': {'workload': WORKLOAD + '; bf16 compute / fp32 master weights',
                        'batch_per_gpu': B, 'global_batch': B * world, 'frames': FRAMES, 'resolution': RES,
-                       'params': n_params, 'parallelism': f'dp{world}',
-                       'launch': 'whole step replayed as one CUDA graph' if use_graph else 'eager launches',
+                       'params': n_params, 'parallelism': f'dp{world}', 'launch': launch,
+                       'grad_exchange': None if reducer is None else
+                       f'NCCL all-reduce (AVG) in place on the zero arena, {reducer.bucket >> 20} MB ranges overlapped with '
+                       f'backward, {reducer.grad_bytes()} B per step',
                        'l2': 'no flush: every step streams several GB of activations (>> 126 MB L2)'},
             'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes * world,
-                    'd2h_bytes_per_step': 4 * world},
+                    'd2h_bytes_per_step': 4 * world,
+                    'legs_ms': [ms_e2e_a / args.steps, ms_e2e_b / args.steps],
+                    'note': 'mean of two K-step legs bracketing the device-resident leg'},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads, avail = pick_cpu_threads()
-            step = cpu_train_step_factory(args.cpu_batch)
+            threads, avail, probe = pick_cpu_threads()
+            step, kind = cpu_train_step_factory(args.cpu_batch)
             t0 = time.perf_counter()
             step()
             dt = time.perf_counter() - t0
             line['cpu_baseline'] = {
-                'value': args.cpu_batch * FRAMES / dt, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                'sample': f'one training step on {args.cpu_batch} clip(s) ({dt:.1f} s), fp32 torch CPU, '
-                          f'{threads} threads (fastest of {avail} available), oracle port of the reference'}
+                'value': args.cpu_batch * FRAMES / dt, 'unit': 'frames/s', 'cores': threads, 'cores_usable': avail,
+                'kind': kind, 'thread_probe_ms': probe,
+                'sample': f'one training step ({dt:.1f} s): ' + cpu_sample_text(args.cpu_batch, threads, avail, kind)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -95,10 +95,23 @@ def launch_count() -> int:
     return int(load().og_launch_count())
 
 
+# Optional per-launch timing of EVERY entry point (bench.py's per-kernel roofline table): when TIMING is a list,
+# each call appends (name, args, start_event, end_event) — CUDA events on the launching stream, no syncs.
+TIMING = None
+
+
 def call(name: str, *args):
     """Call an int-returning entry point; raise on a non-zero status."""
     fn = getattr(load(), name)
-    rc = fn(*args)
+    if TIMING is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TIMING.append((name, args, e0, e1))
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise RuntimeError(f'{name} failed (status {rc}): {last_error()}')
     return rc

@@ -19,9 +19,13 @@ __global__ void og_embed_add_fwd_kernel(const long long* __restrict__ tok, const
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / cv;
     const int c = (int)(i % cv) * 8;
-    long long t = tok[row], a = act[row / rows_per_act];
-    t = t < 0 ? 0 : (t >= tok_vocab ? tok_vocab - 1 : t);  // PyTorch would raise; clamp instead of faulting
-    a = a < 0 ? 0 : (a >= act_vocab ? act_vocab - 1 : a);
+    const long long t = tok[row], a = act[row / rows_per_act];
+    if (t < 0 || t >= tok_vocab || a < 0 || a >= act_vocab) {
+      // nn.Embedding raises a device-side assert on an out-of-range index (dynamics.py:34-38); so does this kernel
+      if (c == 0) printf("og_embed_add_fwd: index out of range (token %lld / vocab %d, action %lld / vocab %d)\n", t,
+                         tok_vocab, a, act_vocab);
+      __trap();
+    }
     const float4* tp = reinterpret_cast<const float4*>(tok_w + t * C + c);
     const float4* ap = reinterpret_cast<const float4*>(act_w + a * C + c);
     const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), a0 = __ldg(ap), a1 = __ldg(ap + 1);
@@ -80,8 +84,11 @@ __global__ void og_masked_ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float lse = m + __logf(s);
     if (lane == 0) {
-      long long t = target[row];
-      t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+      const long long t = target[row];
+      if (t < 0 || t >= V) {  // F.cross_entropy raises a device-side assert on a target outside [0, V) (dynamics.py:97)
+        printf("og_masked_ce_fwd: target %lld out of range [0, %d)\n", t, V);
+        __trap();
+      }
       row_lse[row] = lse;
       loss_acc += lse - __bfloat162float(lp[t]);
       cnt += 1.f;

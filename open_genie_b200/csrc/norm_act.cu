@@ -69,7 +69,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 // statistics: grid (chunks, N); block 256. Thread -> (channel vector cv, row lane rl).
 // ------------------------------------------------------------------------------------------------
-static constexpr int kStatRows = 256;  // granularity of the row ranges handed to a block
+static constexpr int kStatRows = 16;  // granularity of the row ranges handed to a block. (It was 256: the 512-channel
+// 4x8x8 stage has V = 256 rows per sample, i.e. ONE block per sample = 8 CTAs on 148 SMs, each walking 64 dependent
+// iterations — 62 such launches per pass made the low-resolution stages cost as much as the 16x64x64 ones.)
 
 // grid (blocks_per_sample, N); each block owns a contiguous row range of one sample and keeps fp32 partial
 // sums in registers over the whole range (4 independent 16-byte loads in flight per thread), then one

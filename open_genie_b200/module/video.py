@@ -52,6 +52,16 @@ class Conv3dParams(nn.Module):
         self._fused_into = None     # weakref to the conv whose operand matrix carries this shortcut
         CONV_REGISTRY[id(self.weight)] = self
 
+    def __setstate__(self, state):
+        """copy.deepcopy / pickle (EMA copies, ddp_spawn): the copy owns NEW Parameter objects, so it must register
+        itself (FusedAdamW finds the bf16 operand of a weight through CONV_REGISTRY) and rebuild its packed operand;
+        the owning block re-links fused shortcuts (a deep-copied weakref still points at the ORIGINAL module)."""
+        super().__setstate__(state)
+        self._packed = None
+        self._packed_key = None
+        object.__setattr__(self, '_fused_into', None)
+        CONV_REGISTRY[id(self.weight)] = self
+
     def fuse_shortcut(self, other: 'Conv3dParams'):
         """Append `other` (a 1x1x1 conv on a second input) as extra K columns of the packed operand, so
         main(x) + res(x) (genie/module/video.py:648) is ONE implicit GEMM with one accumulator."""
@@ -277,6 +287,10 @@ class VideoResidualBlock(nn.Module):
         self.main[6].fuse_shortcut(self.res[1])
         self.inp_channels, self.out_channels = in_channels, out_channels
         self.in_channels = in_channels
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.main[6].fuse_shortcut(self.res[1])     # re-link inside the copy (see Conv3dParams.__setstate__)
 
     def forward(self, inp: Tensor) -> Tensor:
         fusable = all((c // self.main[0].num_groups) % 8 == 0 for c in (self.inp_channels, self.out_channels))

@@ -23,72 +23,179 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-_WS = {}
 # ------------------------------------------------------------------------------------------------
-# step-scoped zero arena
+# step-scoped zero arena + split-K workspace, both owned by a "step scope"
 # ------------------------------------------------------------------------------------------------
-class _ZeroArena:
-    """Bump allocator for the zero-initialised accumulators of one training step (weight-gradient buffers the
-    wgrad kernel reduces into, bias / gamma / beta gradients, GroupNorm sums): ONE fill of the extent used by the
-    previous step replaces ~540 small fill launches per tokenizer step.
+def _in_backward() -> bool:
+    """True while autograd is executing a backward graph on this thread (custom Function.backward runs with grad
+    mode OFF, so torch.is_grad_enabled() cannot tell a backward pass from a no_grad forward)."""
+    return torch._C._current_graph_task_id() != -1
 
-    Contract (why it is opt-in — `enable_zero_arena()`; `GraphedTrainStep` turns it on): everything handed out
-    is valid until the first allocation after the next `mark_step()` (called by `FusedAdamW.step()`), so
-    gradients must be released with `zero_grad(set_to_none=True)` every step and must not be kept across steps.
-    Loss values are never placed here."""
+
+class ZeroArena:
+    """Bump allocator for the zero-initialised accumulators of ONE training step (the fp32 buffers the weight-
+    gradient kernel reduces into, bias / gamma / beta gradients, GroupNorm sums and reduction buffers): one fill of
+    the extent used by the previous step replaces ~540 small fill launches, and — because every parameter gradient
+    of the step then lives in one contiguous range — the data-parallel all-reduce runs directly on slices of it
+    (ddp.ArenaGradAllReducer): no bucket copies.
+
+    Lifetime contract: everything handed out is valid until the first allocation after the next `mark_step()`
+    (FusedAdamW.step() calls it), so gradients must be released with `zero_grad(set_to_none=True)` every step.
+    Only allocations made while a gradient can exist are served (grad mode on, or inside backward); a no_grad /
+    inference forward gets plain torch.zeros, so it can never see or disturb a step's accumulators.
+
+    Memory is a list of segments: the first step of a model grows it segment by segment; the next step boundary
+    consolidates it into one buffer (never while a CUDA graph is being captured, and never again once `frozen` —
+    a captured graph has the addresses baked in)."""
+
+    SEGMENT = 256 << 20
 
     def __init__(self):
-        self.enabled = False
-        self.buf = {}        # device -> uint8 tensor
-        self.off = {}        # device -> bytes handed out this step
-        self.want = {}       # device -> bytes requested this step (including what did not fit)
+        self.segs = {}       # device -> [uint8 tensors]
+        self.cur = {}        # device -> (segment index, byte offset) of the next allocation
+        self.hi = {}         # device -> [bytes used per segment] in the current step
+        self.bwd0 = {}       # device -> (segment, offset) of the first allocation made inside backward this step
         self.dirty = {}      # device -> a step boundary passed since the last allocation
+        self.frozen = False
 
+    # -- step boundary ---------------------------------------------------------------------------
     def mark_step(self):
         for d in self.dirty:
             self.dirty[d] = True
 
     def _begin(self, dev):
-        used, want = self.off.get(dev, 0), self.want.get(dev, 0)
-        buf = self.buf.get(dev)
+        segs = self.segs.setdefault(dev, [])
+        used = self.hi.get(dev, [])
         capturing = dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()
-        if (buf is None or want > buf.numel()) and want > 0 and not capturing:
-            # (capped: a long run of forward-only calls between two optimizer steps must not balloon the arena)
-            buf = torch.zeros(min(int(want * 1.05) + 65536, 16 << 30), dtype=torch.uint8, device=dev)   # fresh: already zero
-            self.buf[dev] = buf
-        elif buf is not None and used > 0:
-            buf[:used].zero_()
-        self.off[dev], self.want[dev], self.dirty[dev] = 0, 0, False
+        if len(segs) > 1 and not capturing and not self.frozen:
+            total = sum(used)
+            segs[:] = [torch.zeros(min(int(total * 1.05) + (1 << 20), 32 << 30), dtype=torch.uint8, device=dev)]
+        else:
+            for t, u in zip(segs, used):
+                if u:
+                    t[:u].zero_()
+        self.cur[dev] = (0, 0)
+        self.hi[dev] = [0] * len(segs)
+        self.bwd0.pop(dev, None)
+        self.dirty[dev] = False
 
+    # -- allocation ------------------------------------------------------------------------------
     def zeros(self, shape, dtype, device):
-        if not self.enabled:
-            return torch.zeros(shape, dtype=dtype, device=device)
         dev = torch.device(device)
+        if dev.type == 'cuda' and dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
         if self.dirty.setdefault(dev, True):
             self._begin(dev)
         n = 1
-        for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+        for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
             n *= int(d)
         nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if nbytes == 0:
+            return torch.zeros(shape, dtype=dtype, device=dev)
         al = (nbytes + 255) & ~255
-        self.want[dev] = self.want.get(dev, 0) + al
-        buf, off = self.buf.get(dev), self.off.get(dev, 0)
-        if buf is None or off + al > buf.numel() or nbytes == 0:
-            return torch.zeros(shape, dtype=dtype, device=device)
-        self.off[dev] = off + al
-        return buf[off:off + nbytes].view(dtype).view(shape)
+        segs, hi = self.segs[dev], self.hi[dev]
+        si, off = self.cur[dev]
+        while si < len(segs) and off + al > segs[si].numel():
+            si, off = si + 1, 0
+        if si == len(segs):
+            capturing = dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()
+            if self.frozen or capturing:
+                raise RuntimeError('open_genie_b200: the zero arena of a captured training step is too small for this '
+                                   'step (shapes changed after capture?) — re-create the GraphedTrainStep')
+            segs.append(torch.zeros(max(self.SEGMENT, al), dtype=torch.uint8, device=dev))   # fresh: already zero
+            hi.append(0)
+        if dev not in self.bwd0 and _in_backward():
+            self.bwd0[dev] = (si, off)
+        self.cur[dev] = (si, off + al)
+        hi[si] = off + al
+        return segs[si][off:off + nbytes].view(dtype).view(shape)
+
+    # -- introspection (ddp.ArenaGradAllReducer, tests) ------------------------------------------
+    def position(self, dev):
+        return self.cur.get(torch.device(dev), (0, 0))
+
+    def locate(self, t: Tensor):
+        """(segment, byte offset) of tensor `t` if its storage lies inside this arena, else None."""
+        p = t.data_ptr()
+        for si, s in enumerate(self.segs.get(t.device, [])):
+            o = p - s.data_ptr()
+            if 0 <= o < s.numel():
+                return si, o
+        return None
+
+    def bytes_in_use(self, dev=None):
+        return sum(sum(v) for d, v in self.hi.items() if dev is None or d == torch.device(dev))
 
 
-ZERO_ARENA = _ZeroArena()
+class StepScope:
+    """The mutable scratch a training step's kernels use: the zero arena and the split-K workspace. The process has
+    one default scope (arena off unless enable_zero_arena()); a GraphedTrainStep owns a PRIVATE scope that is never
+    reallocated or freed while its graph is alive, so eager calls made later (validation, tokenize(), a bigger
+    batch) cannot free or overwrite memory whose address is baked into the captured graph."""
+
+    def __init__(self, arena: Optional[ZeroArena] = None):
+        self.arena = arena
+        self.ws = {}          # device -> uint8 workspace
+        self.frozen = False
+
+    def workspace(self, dev, nbytes: int):
+        nbytes = min(max(nbytes, 1 << 20), 1 << 30)
+        t = self.ws.get(dev)
+        if t is None or t.numel() < nbytes:
+            if self.frozen or (dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()):
+                raise RuntimeError('open_genie_b200: split-K workspace of a captured training step would have to grow')
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.ws[dev] = t
+        return t
+
+    def freeze(self):
+        self.frozen = True
+        if self.arena is not None:
+            self.arena.frozen = True
+
+
+_DEFAULT_SCOPE = StepScope()
+_SCOPE = _DEFAULT_SCOPE
+ZERO_ARENA = ZeroArena()      # the default scope's arena when enable_zero_arena(True)
+
+
+class step_scope:
+    """`with ops.step_scope(scope): ...` — route arena / workspace allocations to `scope`."""
+
+    def __init__(self, scope: StepScope):
+        self.scope = scope
+
+    def __enter__(self):
+        global _SCOPE
+        self.prev, _SCOPE = _SCOPE, self.scope
+        return self.scope
+
+    def __exit__(self, *exc):
+        global _SCOPE
+        _SCOPE = self.prev
+        return False
 
 
 def enable_zero_arena(on: bool = True):
-    """Opt in to the step-scoped zero arena (see _ZeroArena for the lifetime contract)."""
-    ZERO_ARENA.enabled = bool(on)
+    """Opt in to the step-scoped zero arena for eagerly launched training steps (see ZeroArena for the contract)."""
+    _DEFAULT_SCOPE.arena = ZERO_ARENA if on else None
+
+
+def current_arena() -> Optional[ZeroArena]:
+    return _SCOPE.arena
+
+
+def mark_step():
+    """A training step ended (gradients consumed): the current scope's arena may be recycled."""
+    if _SCOPE.arena is not None:
+        _SCOPE.arena.mark_step()
 
 
 def _zeros(shape, dtype, device):
-    return ZERO_ARENA.zeros(shape, dtype, device)
+    a = _SCOPE.arena
+    if a is None or not (torch.is_grad_enabled() or _in_backward()):
+        return torch.zeros(shape, dtype=dtype, device=device)
+    return a.zeros(shape, dtype, device)
 
 
 # tuning switches (environment): fuse GroupNorm statistics / backward reductions into the GEMM epilogues
@@ -98,14 +205,9 @@ FUSE_RED = _os.environ.get('OG_FUSE_RED', '0') != '0'   # measured: costs more i
 
 
 def _workspace(dev, nbytes: int):
-    """Reusable fp32 scratch for split-K convolutions (small T*H*W, deep K). One buffer per device; every use
-    is stream-ordered (memset -> partial sums -> finish pass inside one og_conv3d_* call)."""
-    nbytes = min(max(nbytes, 1 << 20), 1 << 30)
-    t = _WS.get(dev)
-    if t is None or t.numel() < nbytes:
-        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _WS[dev] = t
-    return t
+    """Reusable fp32 scratch for split-K convolutions (small T*H*W, deep K). One buffer per device and step scope;
+    every use is stream-ordered (memset -> partial sums -> finish pass inside one og_conv3d_* call)."""
+    return _SCOPE.workspace(dev, nbytes)
 
 
 # Optional per-launch timing of the tensor-core kernels (bench.py's roofline): when PROFILE is a list, every
@@ -807,6 +909,12 @@ class _EmbedAddFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tokens, act_id, tok_w, act_w):
         _require_cuda(tok_w, 'embedding weight')
+        if tokens.dim() != 4:
+            raise ValueError(f'embed_add: tokens must be (B, T, H, W), got {tuple(tokens.shape)}')
+        if tuple(act_id.shape) != tuple(tokens.shape[:2]):
+            # the reference adds act_emb (b,t,1,1,d) to tok_emb (b,t,h,w,d) (dynamics.py:55): mismatched t raises there
+            raise ValueError(f'embed_add: act_id shape {tuple(act_id.shape)} does not match the (B, T) = '
+                             f'{tuple(tokens.shape[:2])} of the tokens (one action per token frame)')
         B, T, H, W = tokens.shape
         C = tok_w.shape[1]
         tok = tokens.detach().to(torch.int64).contiguous()

@@ -16,14 +16,53 @@ class FusedAdamW(Optimizer):
     def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, bf16_targets: Optional[dict] = None):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._step = 0
+        self._step = 0                                   # host mirror of the step count (eager launches)
         self._cache_key = None
         self._size_key = None
         self._dev_table = self._dev_ct = self._dev_ci = None
         self._num_chunks = 0
         self.grad_scale: Optional[torch.Tensor] = None   # device scalar multiplied into every gradient
-        self._step_dev: Optional[torch.Tensor] = None    # device-side step counter (CUDA-graph safe)
+        self._step_dev: Optional[torch.Tensor] = None    # device-side step counter (CUDA-graph safe, authoritative)
+        self._lr_dev = {}                                # id(group) -> (device scalar, host value it holds)
         self._pinned = []                                # host staging buffers referenced by captured copies
+
+    # ---- step count / learning rate live on the device so a captured step stays exact -------------------
+    def step_count(self) -> int:
+        """Number of optimizer steps taken (reads the device counter: replays of a captured step advance it
+        without running any Python)."""
+        if self._step_dev is not None:
+            self._step = int(self._step_dev.item())
+        return self._step
+
+    def sync_lr(self):
+        """Copy each group's current `lr` (as set by an LR scheduler) into the device scalar the kernel reads.
+        Called by step() when launching eagerly and by GraphedTrainStep before every replay; never captured."""
+        for group in self.param_groups:
+            ent = self._lr_dev.get(id(group))
+            if ent is None:
+                continue
+            t, held = ent
+            lr = float(group['lr'])
+            if lr != held:
+                t.fill_(lr)
+                self._lr_dev[id(group)] = (t, lr)
+
+    def state_dict(self):
+        """torch.optim.AdamW layout: every state entry carries 'step' (fp32 scalar tensor) next to exp_avg /
+        exp_avg_sq, so checkpoints interchange with the reference's optimizer (genie/tokenizer.py:250,437-442)."""
+        n = self.step_count()
+        for st in self.state.values():
+            if st:
+                st['step'] = torch.tensor(float(n))
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        steps = [int(st['step']) for st in self.state.values() if st and 'step' in st]
+        self._step = max(steps) if steps else 0
+        if self._step_dev is not None:
+            self._step_dev.fill_(self._step)
+        self._cache_key = None
 
     def _bf16_target(self, p):
         """Packed bf16 operand (tensor, column offset) of the conv that owns parameter p, if any."""
@@ -46,7 +85,10 @@ class FusedAdamW(Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
-        loss = closure() if closure is not None else None
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():       # like torch.optim: Lightning's closure runs training_step + backward
+                loss = closure()
         entries = []
         for group in self.param_groups:
             for p in group['params']:
@@ -75,7 +117,7 @@ class FusedAdamW(Optimizer):
         for ents in by_group.values():
             self._launch(ents)
         from . import ops
-        ops.ZERO_ARENA.mark_step()          # gradients consumed: the step-scoped zero arena may be recycled
+        ops.mark_step()                     # gradients consumed: the step-scoped zero arena may be recycled
         return loss
 
     def _launch(self, ents):
@@ -117,7 +159,13 @@ class FusedAdamW(Optimizer):
             self._cache_key = key
         b1, b2 = group['betas']
         stream = torch.cuda.current_stream().cuda_stream
+        if id(group) not in self._lr_dev:
+            lr0 = float(group['lr'])
+            self._lr_dev[id(group)] = (torch.full((1,), lr0, dtype=torch.float32, device=ents[0][0].device), lr0)
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
         _lib.call('og_adamw_step', self._dev_table.data_ptr(), self._dev_ct.data_ptr(), self._dev_ci.data_ptr(),
                   self._num_chunks, float(group['lr']), float(b1), float(b2), float(group['eps']),
-                  float(group['weight_decay']), self._step, self._step_dev.data_ptr(), None,
+                  float(group['weight_decay']), self._step, self._step_dev.data_ptr(),
+                  self._lr_dev[id(group)][0].data_ptr(),
                   None if self.grad_scale is None else self.grad_scale.data_ptr(), stream)

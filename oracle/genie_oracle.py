@@ -59,6 +59,15 @@ def det_uniform(key: str, shape: Sequence[int], scale: float = 1.0) -> Tensor:
     return torch.from_numpy(v.astype(np.float32)).reshape(tuple(shape))
 
 
+def det_indices(key: str, numel: int, n: int = 1024) -> Tensor:
+    """n deterministic flat indices into a tensor of `numel` elements (all of them when numel <= n): the sample
+    on which the full-size goldens store / compare big gradients."""
+    if numel <= n:
+        return torch.arange(numel)
+    u = det_uniform('idx.' + key, (n,)) / math.sqrt(3.0)           # (-1, 1)
+    return ((u.double() + 1.0) * 0.5 * numel).long().clamp_(0, numel - 1)
+
+
 def det_state_dict(shapes: Dict[str, Sequence[int]], gain: float = 1.0) -> StateDict:
     """Deterministic weights for a reference-format state_dict (shapes from the reference module).
 

@@ -313,12 +313,12 @@ def test_zero_arena_gradients_match_plain_allocation():
         ops.enable_zero_arena(True)
         for it in range(3):
             m.zero_grad(set_to_none=True)          # the arena contract: gradients are released every step
-            ops.ZERO_ARENA.mark_step()
+            ops.mark_step()
             y1, dx1, g1 = _run_layer(m, x)
             assert_close(y1, y0, BF16_ULP, BF16_ULP * y0.abs().max().item(), f'arena fwd (step {it})')
             assert_close(dx1, dx0, 2 * BF16_ULP, 2 * BF16_ULP * dx0.abs().max().item(), f'arena dx (step {it})')
             for k in g0:
                 assert_close(g1[k], g0[k], 2e-3, 2e-3 * g0[k].abs().max().item(), f'arena grad {k} (step {it})')
-        assert any(v > 0 for v in ops.ZERO_ARENA.off.values())             # the arena was really used
+        assert ops.ZERO_ARENA.bytes_in_use() > 0                           # the arena was really used
     finally:
         ops.enable_zero_arena(False)

@@ -82,23 +82,79 @@ def test_shard_batch_partitions_clips():
 
 
 def test_zero_arena_lifetime_contract():
-    """ops._ZeroArena: first step only measures, later steps hand out zeroed views of one buffer; a view is
+    """ops.ZeroArena: zeroed views of segment memory; the step after the first consolidates into one buffer; a view is
     recycled (and re-zeroed) by the first allocation after mark_step()."""
     import torch
     from open_genie_b200 import ops
-    a = ops._ZeroArena()
-    assert a.zeros((2, 3), torch.float32, 'cpu').data_ptr() != 0          # disabled: plain torch.zeros
-    a.enabled = True
-    x = a.zeros((3, 4), torch.float32, 'cpu')                               # step 1: nothing to carve from yet
-    assert a.buf.get(torch.device('cpu')) is None and x.sum() == 0
+    a = ops.ZeroArena()
+    a.SEGMENT = 4096                                                          # small segments: force growth
+    x = a.zeros((3, 4), torch.float32, 'cpu')
+    big = a.zeros((4096,), torch.float32, 'cpu')                              # does not fit: a second segment
+    assert x.sum() == 0 and big.sum() == 0 and len(a.segs[torch.device('cpu')]) == 2
+    assert a.locate(x) == (0, 0) and a.locate(big) == (1, 0)
+    x += 1
+    big += 2
     a.mark_step()
-    y = a.zeros((3, 4), torch.float32, 'cpu')
-    z = a.zeros((5,), torch.float64, 'cpu')
+    y = a.zeros((3, 4), torch.float32, 'cpu')                                 # boundary: consolidated, everything zero
+    z = a.zeros((4096,), torch.float64, 'cpu')
+    assert len(a.segs[torch.device('cpu')]) == 1 and y.sum() == 0 and z.sum() == 0
     assert y.untyped_storage().data_ptr() == z.untyped_storage().data_ptr()  # one buffer
     y += 1
     z += 2
-    big = a.zeros((1 << 20,), torch.float32, 'cpu')                          # does not fit: falls back, grows next step
-    assert big.untyped_storage().data_ptr() != y.untyped_storage().data_ptr()
     a.mark_step()
     w = a.zeros((3, 4), torch.float32, 'cpu')
-    assert w.sum() == 0 and a.buf[torch.device('cpu')].numel() >= 4 << 20
+    assert w.data_ptr() == y.data_ptr() and w.sum() == 0                      # recycled and cleared
+    assert a.bytes_in_use() == 256
+
+
+def test_zero_arena_scoping_contract():
+    """a step's accumulators must never be handed to forward-only / no_grad work, and a private
+    (graph-owned) scope must neither grow nor be shared with the default scope."""
+    import torch
+    from open_genie_b200 import ops
+    ops.enable_zero_arena(True)
+    try:
+        a = ops.current_arena()
+        with torch.no_grad():
+            z = ops._zeros((16,), torch.float32, 'cpu')
+        assert a.locate(z) is None                                  # inference / validation forward: plain torch.zeros
+        g = ops._zeros((16,), torch.float32, 'cpu')                 # grad mode on (training forward): arena
+        assert a.locate(g) is not None
+        g += 1.0
+        ops.mark_step()
+        with torch.no_grad():
+            z2 = ops._zeros((16,), torch.float32, 'cpu')
+        assert a.locate(z2) is None and float(z2.sum()) == 0.0      # even right after a step boundary
+        g2 = ops._zeros((16,), torch.float32, 'cpu')
+        assert float(g2.sum()) == 0.0                               # recycled range was cleared
+        # a private scope (what GraphedTrainStep owns) is separate memory and refuses to grow once frozen
+        scope = ops.StepScope(ops.ZeroArena())
+        with ops.step_scope(scope):
+            p = ops._zeros((1024,), torch.float32, 'cpu')
+            assert scope.arena.locate(p) is not None and a.locate(p) is None
+            ws = ops._workspace(torch.device('cpu'), 1 << 20)
+        scope.freeze()
+        assert ops.current_arena() is a                              # default scope restored
+        with ops.step_scope(scope):
+            ops.mark_step()
+            assert scope.arena.locate(ops._zeros((1024,), torch.float32, 'cpu')) is not None     # same range again
+            assert ops._workspace(torch.device('cpu'), 1 << 20).data_ptr() == ws.data_ptr()
+            import pytest
+            with pytest.raises(RuntimeError, match='too small'):
+                ops._zeros((1 << 28,), torch.float32, 'cpu')
+            with pytest.raises(RuntimeError, match='would have to grow'):
+                ops._workspace(torch.device('cpu'), 1 << 29)
+    finally:
+        ops.enable_zero_arena(False)
+
+
+def test_conv_modules_survive_deepcopy():
+    """a deep copy must register its own weights for the fused optimizer and re-link its fused shortcut."""
+    import copy
+    from open_genie_b200.module.video import CONV_REGISTRY, VideoResidualBlock
+    m = VideoResidualBlock(64, 128)
+    c = copy.deepcopy(m)
+    for mod in (c.main[2], c.main[6], c.res[1]):
+        assert CONV_REGISTRY.get(id(mod.weight)) is mod
+    assert c.main[6]._extra is c.res[1] and c.res[1]._fused_into() is c.main[6]
+    assert m.main[6]._extra is m.res[1] and m.res[1]._fused_into() is m.main[6]
