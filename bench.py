@@ -258,7 +258,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='clips per GPU (BASELINE configs[1]: 8)')
     ap.add_argument('--cpu-batch', type=int, default=2, help='clips per CPU-baseline step (BASELINE.md §3: B = 2)')
-    ap.add_argument('--cpu-budget-s', type=float, default=300.0,
+    ap.add_argument('--cpu-budget-s', type=float, default=400.0,
                     help='--impl reference: drop to 1 clip per step if (steps+warmup) x first-step time exceeds this')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying the captured step')
@@ -413,6 +413,16 @@ def main():
             d['launches'] += 1
         peak_tf = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
         peak_bw = peaks.get('hbm_gbs')
+        # the ten conv problem shapes that cost the most time per step (small-int C-ABI arguments identify the layer)
+        by_shape = {}
+        for kind, flops, a, b, shape in prof:
+            d = by_shape.setdefault((kind,) + tuple(shape), {'ms': 0.0, 'flop': 0.0, 'n': 0})
+            d['ms'] += a.elapsed_time(b)
+            d['flop'] += flops
+            d['n'] += 1
+        top_shapes = [{'kind': k[0], 'args': list(k[1:]), 'launches_per_step': d['n'] / prof_steps,
+                       'ms_per_step': round(d['ms'] / prof_steps, 3), 'tflops': round(d['flop'] / max(d['ms'], 1e-9) * 1e-9, 1)}
+                      for k, d in sorted(by_shape.items(), key=lambda kv: -kv[1]['ms'])[:14]]
         kern = {}
         for k, d in kinds.items():
             tf = d['flop'] / max(d['ms'], 1e-9) * 1e-9
@@ -458,7 +468,7 @@ def main():
                         'unit': 'TFLOP/s', 'frac': kern[dom]['tflops'] / peak_tf, 'traffic': traffic,
                         'traffic_note': traffic_note,
                         'peak_source': peak_src + ' sustained bf16; HBM-bound kernels against hbm_gbs', 'kernels': kern,
-                        'conv_flop_per_step': conv_flop,
+                        'conv_flop_per_step': conv_flop, 'conv_top_shapes': top_shapes,
                         'whole_step': {'tflops': conv_flop / (ms_step * 1e-3) * 1e-12,
                                        'frac': conv_flop / (ms_step * 1e-3) * 1e-12 / peak_tf},
                         'timing': f'CUDA events around each launch over {prof_steps} eagerly launched steps after the '

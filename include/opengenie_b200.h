@@ -176,6 +176,11 @@ int og_col2im3d(const void* dcol, void* dx, int dx_f32, int N, int T, int H, int
 int og_blurpool3d(const void* x, void* y, float* scratch, int backward, int N, int T, int H, int W, int cin, int cout,
                   int k, int st, int sh, int sw, og_stream_t stream);
 
+/* BlurPooling2d with num_groups == 1 (genie/module/image.py:43-85; registry name 'blur_pool'): x [N,H,W,cin] ->
+ * y [N,Ho,Wo,cout], Pascal kernel k x k, stride (sh, sw), symmetric padding `pad` (the reference uses (k-1)//stride). */
+int og_blurpool2d(const void* x, void* y, float* scratch, int backward, int N, int H, int W, int cin, int cout, int k,
+                  int sh, int sw, int pad, og_stream_t stream);
+
 /* mse_loss (tokenizer.py:364, action.py:166): loss_sum += sum (rec - tgt)^2 ; rec NDHWC fp32, tgt NCDHW fp32.
  * Backward writes gscale * 2 (rec - tgt) / numel as bf16 NDHWC with cpad >= C channels (zero padded) so it
  * can feed og_conv3d_dgrad / og_conv3d_wgrad directly. gscale: device scalar or NULL (= 1). */
@@ -275,6 +280,20 @@ int og_masked_ce_fwd(const void* logits, const int64_t* target, const uint8_t* m
                      float* row_lse, float* stats, og_stream_t stream);
 int og_masked_ce_bwd(const void* logits, const int64_t* target, const uint8_t* mask, const float* row_lse,
                      const float* stats, const float* gloss, void* dlogits, int64_t rows, int V, og_stream_t stream);
+
+/* MaskGIT iterative sampling — DynamicsModel.generate (genie/dynamics.py:101-165). The reference packs the
+ * transformer input once before its loop and never updates it (lines 128-134), so all iterations share one set of
+ * logits: og_softmax_cdf turns them into per-position CDFs (softmax(logits / temp), line 143) once, and
+ * og_maskgit_sample runs EVERY iteration of lines 136-163 in one launch (one CTA per batch row): inverse-CDF draw with
+ * the supplied uniforms (torch.multinomial's role, line 145) -> confidence = prob[pred] (146) -> -inf on already
+ * predicted positions (151) -> top-k of `schedule[s]` (152) -> scatter into code / mask (159-160).
+ * logits: [rows = B*P][V] bf16 or fp32; cdf: fp32 [rows][V]; uniforms: fp32 [steps][B][P] in [0,1);
+ * schedule: int32 [steps] (device); code: int64 [B][P] in/out (initialised to masked_tok); mask: uint8 [B][P] in/out
+ * (1 = still to predict). P <= 4096. */
+int og_softmax_cdf(const void* logits, int logits_f32, int64_t rows, int V, float inv_temp, float* cdf,
+                   og_stream_t stream);
+int og_maskgit_sample(const float* cdf, const float* uniforms, const int* schedule, int steps, int B, int P, int V,
+                      int64_t* code, uint8_t* mask, og_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fused multi-tensor AdamW (genie/tokenizer.py:437-442) + bf16 operand refresh

@@ -121,6 +121,127 @@ __global__ void og_masked_ce_bwd_kernel(const __nv_bfloat16* __restrict__ logits
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MaskGIT sampling (DynamicsModel.generate, genie/dynamics.py:101-165)
+//
+// In the reference loop the transformer input `tok_id` is packed ONCE before the loop and never updated (lines
+// 128-134), so every iteration sees the same logits; only the multinomial draws differ. The B200 form therefore
+// evaluates the transformer once, turns the last frame's logits into per-position CDFs once (og_softmax_cdf), and runs
+// ALL sampling iterations in one launch (og_maskgit_sample: one CTA per batch row; per iteration inverse-CDF draw ->
+// confidence -> mask already-predicted positions to -inf -> top-k -> scatter into code / mask).
+// ------------------------------------------------------------------------------------------------
+
+// cdf[row][j] = sum_{i<=j} softmax(logits[row] * inv_temp)[i], fp32; one warp per row.
+__global__ void og_softmax_cdf_kernel(const void* __restrict__ logits, int logits_f32, long long rows, int V, float inv_temp,
+                                      float* __restrict__ cdf) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = w0; row < rows; row += nw) {
+    auto at = [&](int j) -> float {
+      return (logits_f32 ? reinterpret_cast<const float*>(logits)[row * V + j]
+                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(logits)[row * V + j])) * inv_temp;
+    };
+    float m = -INFINITY;
+    for (int j = lane; j < V; j += 32) m = fmaxf(m, at(j));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int j = lane; j < V; j += 32) s += expf(at(j) - m);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.f / s;
+    float carry = 0.f;
+    for (int j0 = 0; j0 < V; j0 += 32) {
+      const int j = j0 + lane;
+      float p = j < V ? expf(at(j) - m) * inv : 0.f;
+      for (int o = 1; o < 32; o <<= 1) {  // inclusive warp scan
+        const float t = __shfl_up_sync(0xffffffffu, p, o);
+        if (lane >= o) p += t;
+      }
+      p += carry;
+      if (j < V) cdf[row * V + j] = p;
+      carry = __shfl_sync(0xffffffffu, p, 31);
+    }
+  }
+}
+
+// One CTA (1024 threads) per batch row; P = h*w positions (P <= 4096).
+__global__ void __launch_bounds__(1024)
+    og_maskgit_sample_kernel(const float* __restrict__ cdf, const float* __restrict__ uniforms, const int* __restrict__ schedule,
+                             int steps, int B, int P, int V, long long* __restrict__ code, unsigned char* __restrict__ mask) {
+  extern __shared__ unsigned char smem_mg[];
+  int Pp = 1;
+  while (Pp < P) Pp <<= 1;
+  float* key = reinterpret_cast<float*>(smem_mg);           // [Pp] confidence
+  int* val = reinterpret_cast<int*>(key + Pp);              // [Pp] position
+  int* pred = val + Pp;                                     // [P] sampled token of every position
+  __shared__ int remaining;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int r = 0;
+    for (int p = 0; p < P; ++p) r += mask[(long long)b * P + p] ? 1 : 0;
+    remaining = r;
+  }
+  __syncthreads();
+  for (int s = 0; s < steps; ++s) {
+    if (remaining == 0) break;                              // `if mask.sum() == 0: break` (line 137)
+    const int k = schedule[s];
+    // draw + confidence (lines 143-151)
+    for (int p = threadIdx.x; p < Pp; p += blockDim.x) {
+      float c = -INFINITY;
+      if (p < P) {
+        const float* row = cdf + ((long long)b * P + p) * V;
+        const float u = uniforms[((long long)s * B + b) * P + p] * row[V - 1];
+        int lo = 0, hi = V - 1;                             // first j with cdf[j] > u
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (row[mid] > u) hi = mid; else lo = mid + 1;
+        }
+        pred[p] = lo;
+        const float pr = row[lo] - (lo > 0 ? row[lo - 1] : 0.f);
+        c = mask[(long long)b * P + p] ? pr : -INFINITY;    // conf[~mask] = -inf (line 151)
+      }
+      key[p] = c;
+      val[p] = p;
+    }
+    __syncthreads();
+    // top-k: bitonic sort by (confidence descending, position ascending)
+    for (int size = 2; size <= Pp; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < Pp; i += blockDim.x) {
+          const int j = i ^ stride;
+          if (j > i) {
+            const bool desc = (i & size) == 0;
+            const float ki = key[i], kj = key[j];
+            const int vi = val[i], vj = val[j];
+            const bool i_first = (ki > kj) || (ki == kj && vi < vj);   // i should precede j in descending order
+            if (desc ? !i_first : i_first) {
+              key[i] = kj; key[j] = ki;
+              val[i] = vj; val[j] = vi;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // scatter the k most confident predictions (lines 154-163)
+    for (int i = threadIdx.x; i < k && i < Pp; i += blockDim.x) {
+      const int p = val[i];
+      if (p < P) {
+        code[(long long)b * P + p] = pred[p];
+        mask[(long long)b * P + p] = 0;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int r = 0;
+      for (int p = 0; p < P; ++p) r += mask[(long long)b * P + p] ? 1 : 0;
+      remaining = r;
+    }
+    __syncthreads();
+  }
+}
+
 static int grid_for(long long total, int block, int per_sm) {
   long long g = (total + block - 1) / block;
   long long cap = (long long)num_sms() * per_sm;
@@ -175,6 +296,34 @@ extern "C" int og_masked_ce_bwd(const void* logits, const int64_t* target, const
   og_masked_ce_bwd_kernel<<<grid_for(rows * V, 256, 16), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)logits, (const long long*)target, mask, row_lse, stats, gloss, (__nv_bfloat16*)dlogits, rows,
       V);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_softmax_cdf(const void* logits, int logits_f32, int64_t rows, int V, float inv_temp, float* cdf,
+                              og_stream_t stream) {
+  OG_REQUIRE(logits && cdf && rows > 0 && V > 0, "softmax_cdf: bad arguments");
+  og_softmax_cdf_kernel<<<grid_for(rows, 8, 8), 256, 0, (cudaStream_t)stream>>>(logits, logits_f32, rows, V, inv_temp, cdf);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_maskgit_sample(const float* cdf, const float* uniforms, const int* schedule, int steps, int B, int P, int V,
+                                 int64_t* code, uint8_t* mask, og_stream_t stream) {
+  OG_REQUIRE(cdf && uniforms && schedule && code && mask && steps > 0 && B > 0 && V > 0, "maskgit_sample: bad arguments");
+  OG_REQUIRE(P > 0 && P <= 4096, "maskgit_sample: P=%d positions per frame must be in [1, 4096]", P);
+  int Pp = 1;
+  while (Pp < P) Pp <<= 1;
+  const size_t smem = (size_t)Pp * 8 + (size_t)P * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_maskgit_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  og_maskgit_sample_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(cdf, uniforms, schedule, steps, B, P, V,
+                                                                   (long long*)code, mask);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;

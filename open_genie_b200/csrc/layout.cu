@@ -112,6 +112,30 @@ __global__ void og_pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ x, __n
   }
 }
 
+// Any channel count (REPR_TOK_DEC ends in out_channels = 3, genie/tokenizer.py:196-204): one thread per output element.
+__global__ void og_pixel_shuffle_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int T,
+                                               int H, int W, int c, int p, int q, int r, long long total, int inverse) {
+  const int pqr = p * q * r;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    long long o = i / c;  // output voxel index over [N, T*p, H*q, W*r]
+    const int wo = (int)(o % (W * r));
+    o /= (W * r);
+    const int ho = (int)(o % (H * q));
+    o /= (H * q);
+    const int to = (int)(o % (T * p));
+    const int n = (int)(o / (T * p));
+    const int t = to / p, pp = to % p, h = ho / q, qq = ho % q, w = wo / r, rr = wo % r;
+    const long long vin = (((long long)n * T + t) * H + h) * W + w;
+    const long long xi = vin * ((long long)c * pqr) + (long long)ch * pqr + (pp * q + qq) * r + rr;
+    if (!inverse)
+      y[i] = x[xi];
+    else
+      const_cast<__nv_bfloat16*>(x)[xi] = y[i];
+  }
+}
+
 // Vector form for p*q*r in {2, 4, 8}: one thread owns 8 consecutive output channels of ONE input voxel, i.e. a
 // contiguous run of 8*PQR input channels (PQR 16-byte loads), transposes the 8 x PQR block in registers and
 // writes one 16-byte vector to each of the PQR output voxels. Loads and stores are both fully coalesced; the
@@ -547,7 +571,15 @@ extern "C" int og_ndhwc_to_ncdhw_f32(const void* x, int x_f32, float* y, int N, 
 extern "C" int og_pixel_shuffle3d(const void* x, void* y, int inverse, int N, int T, int H, int W, int c, int p,
                                   int q, int r, og_stream_t stream) {
   OG_REQUIRE(x && y, "pixel_shuffle3d: null pointer");
-  OG_REQUIRE(c % 8 == 0 && p >= 1 && q >= 1 && r >= 1, "pixel_shuffle3d: c=%d must be a multiple of 8", c);
+  OG_REQUIRE(c >= 1 && p >= 1 && q >= 1 && r >= 1, "pixel_shuffle3d: bad shape (c=%d p=%d q=%d r=%d)", c, p, q, r);
+  if (c % 8 != 0) {
+    const long long tot = (long long)N * T * p * H * q * W * r * c;
+    og_pixel_shuffle_scalar_kernel<<<ew_blocks(tot, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, T, H, W, c, p, q, r, tot, inverse);
+    OG_CHECK_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return OG_OK;
+  }
   const long long total = (long long)N * T * p * H * q * W * r * (c / 8);
   // forward: x un-shuffled (read), y shuffled (written). inverse: y shuffled (read), x un-shuffled (written).
   const int pqr = p * q * r;
@@ -704,9 +736,8 @@ __device__ __forceinline__ float pascal(int k, int i) {  // binomial(k-1, i)
 // forward stencil + broadcast: one thread per (output voxel, 8-channel vector)
 __global__ void og_blur3d_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ y, int T, int H, int W,
                                      int To, int Ho, int Wo, int k, int st, int sh, int sw, int Cout, float norm,
-                                     long long total_vec) {
+                                     long long total_vec, int kt, int pad_t, int pad) {
   const int cv = Cout >> 3;
-  const int pad = (k - 1) / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
     long long vo = i / cv;
@@ -717,8 +748,8 @@ __global__ void og_blur3d_fwd_kernel(const float* __restrict__ s, __nv_bfloat16*
     const int to = (int)(r % To);
     const int n = (int)(r / To);
     float acc = 0.f;
-    for (int it = 0; it < k; ++it) {
-      const int t = to * st + it - pad;
+    for (int it = 0; it < kt; ++it) {
+      const int t = to * st + it - pad_t;
       if (t < 0 || t >= T) continue;
       for (int ih = 0; ih < k; ++ih) {
         const int h = ho * sh + ih - pad;
@@ -726,7 +757,7 @@ __global__ void og_blur3d_fwd_kernel(const float* __restrict__ s, __nv_bfloat16*
         for (int iw = 0; iw < k; ++iw) {
           const int w = wo * sw + iw - pad;
           if (w < 0 || w >= W) continue;
-          acc += pascal(k, it) * pascal(k, ih) * pascal(k, iw) * s[(((long long)n * T + t) * H + h) * W + w];
+          acc += pascal(kt, it) * pascal(k, ih) * pascal(k, iw) * s[(((long long)n * T + t) * H + h) * W + w];
         }
       }
     }
@@ -739,9 +770,8 @@ __global__ void og_blur3d_fwd_kernel(const float* __restrict__ s, __nv_bfloat16*
 // adjoint stencil + broadcast: one thread per (input voxel, 8-channel vector)
 __global__ void og_blur3d_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ dx, int T, int H, int W,
                                      int To, int Ho, int Wo, int k, int st, int sh, int sw, int Cin, float norm,
-                                     long long total_vec) {
+                                     long long total_vec, int kt, int pad_t, int pad) {
   const int cv = Cin >> 3;
-  const int pad = (k - 1) / 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
        i += (long long)gridDim.x * blockDim.x) {
     long long v = i / cv;
@@ -752,8 +782,8 @@ __global__ void og_blur3d_bwd_kernel(const float* __restrict__ g, __nv_bfloat16*
     const int t = (int)(r % T);
     const int n = (int)(r / T);
     float acc = 0.f;
-    for (int it = 0; it < k; ++it) {
-      const int tn = t + pad - it;
+    for (int it = 0; it < kt; ++it) {
+      const int tn = t + pad_t - it;
       if (tn < 0 || tn % st || tn / st >= To) continue;
       for (int ih = 0; ih < k; ++ih) {
         const int hn = h + pad - ih;
@@ -761,7 +791,7 @@ __global__ void og_blur3d_bwd_kernel(const float* __restrict__ g, __nv_bfloat16*
         for (int iw = 0; iw < k; ++iw) {
           const int wn = w + pad - iw;
           if (wn < 0 || wn % sw || wn / sw >= Wo) continue;
-          acc += pascal(k, it) * pascal(k, ih) * pascal(k, iw) *
+          acc += pascal(kt, it) * pascal(k, ih) * pascal(k, iw) *
                  g[(((long long)n * To + tn / st) * Ho + hn / sh) * Wo + wn / sw];
         }
       }
@@ -774,20 +804,24 @@ __global__ void og_blur3d_bwd_kernel(const float* __restrict__ g, __nv_bfloat16*
 
 }  // namespace og
 
-extern "C" int og_blurpool3d(const void* x, void* y, float* scratch, int backward, int N, int T, int H, int W, int cin,
-                             int cout, int k, int st, int sh, int sw, og_stream_t stream) {
+static int blurpool_launch(const void* x, void* y, float* scratch, int backward, int N, int T, int H, int W, int cin,
+                           int cout, int kt, int k, int st, int sh, int sw, int pad_t, int pad, og_stream_t stream) {
   using namespace og;
-  OG_REQUIRE(x && y && scratch, "blurpool3d: null pointer");
-  OG_REQUIRE(cin % 8 == 0 && cout % 8 == 0 && k >= 1 && k <= 7 && (k & 1), "blurpool3d: need C %% 8 == 0 and odd k <= 7");
-  const int pad = (k - 1) / 2;
-  const int To = (T + 2 * pad - k) / st + 1, Ho = (H + 2 * pad - k) / sh + 1, Wo = (W + 2 * pad - k) / sw + 1;
-  float ksum = 0.f;
-  for (int i = 0; i < k; ++i) {
-    float v = 1.f;
-    for (int j = 0; j < i; ++j) v = v * (float)(k - 1 - j) / (float)(j + 1);
-    ksum += v;
-  }
-  const float norm = 1.f / (ksum * ksum * ksum);
+  OG_REQUIRE(x && y && scratch, "blurpool: null pointer");
+  OG_REQUIRE(cin % 8 == 0 && cout % 8 == 0 && k >= 1 && k <= 7 && kt >= 1 && kt <= 7, "blurpool: need C %% 8 == 0 and k <= 7");
+  OG_REQUIRE(pad_t >= 0 && pad >= 0 && st >= 1 && sh >= 1 && sw >= 1, "blurpool: bad stride / padding");
+  const int To = (T + 2 * pad_t - kt) / st + 1, Ho = (H + 2 * pad - k) / sh + 1, Wo = (W + 2 * pad - k) / sw + 1;
+  OG_REQUIRE(To >= 1 && Ho >= 1 && Wo >= 1, "blurpool: empty output");
+  auto row_sum = [](int kk) {
+    float t = 0.f;
+    for (int i = 0; i < kk; ++i) {
+      float v = 1.f;
+      for (int j = 0; j < i; ++j) v = v * (float)(kk - 1 - j) / (float)(j + 1);
+      t += v;
+    }
+    return t;
+  };
+  const float norm = 1.f / (row_sum(kt) * row_sum(k) * row_sum(k));
   cudaStream_t s = (cudaStream_t)stream;
   if (!backward) {
     // x: [N,T,H,W,cin] -> y: [N,To,Ho,Wo,cout]; scratch: N*T*H*W floats
@@ -796,7 +830,7 @@ extern "C" int og_blurpool3d(const void* x, void* y, float* scratch, int backwar
     OG_CHECK_CUDA(cudaGetLastError());
     const long long total = (long long)N * To * Ho * Wo * (cout / 8);
     og_blur3d_fwd_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(scratch, (__nv_bfloat16*)y, T, H, W, To, Ho, Wo, k, st, sh,
-                                                              sw, cout, norm, total);
+                                                              sw, cout, norm, total, kt, pad_t, pad);
   } else {
     // x: dy [N,To,Ho,Wo,cout] -> y: dx [N,T,H,W,cin]; scratch: N*To*Ho*Wo floats
     const long long rows = (long long)N * To * Ho * Wo;
@@ -804,9 +838,21 @@ extern "C" int og_blurpool3d(const void* x, void* y, float* scratch, int backwar
     OG_CHECK_CUDA(cudaGetLastError());
     const long long total = (long long)N * T * H * W * (cin / 8);
     og_blur3d_bwd_kernel<<<ew_blocks(total, 256), 256, 0, s>>>(scratch, (__nv_bfloat16*)y, T, H, W, To, Ho, Wo, k, st, sh,
-                                                              sw, cin, norm, total);
+                                                              sw, cin, norm, total, kt, pad_t, pad);
   }
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(2);
   return OG_OK;
 }
+
+extern "C" int og_blurpool3d(const void* x, void* y, float* scratch, int backward, int N, int T, int H, int W, int cin,
+                             int cout, int k, int st, int sh, int sw, og_stream_t stream) {
+  OG_REQUIRE((k & 1) == 1, "blurpool3d: odd kernel sizes only (k=%d)", k);
+  return blurpool_launch(x, y, scratch, backward, N, T, H, W, cin, cout, k, k, st, sh, sw, (k - 1) / 2, (k - 1) / 2, stream);
+}
+
+extern "C" int og_blurpool2d(const void* x, void* y, float* scratch, int backward, int N, int H, int W, int cin, int cout,
+                             int k, int sh, int sw, int pad, og_stream_t stream) {
+  return blurpool_launch(x, y, scratch, backward, N, 1, H, W, cin, cout, 1, k, 1, sh, sw, 0, pad, stream);
+}
+

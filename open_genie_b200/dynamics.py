@@ -5,7 +5,7 @@ signatures, return values and state_dict keys (tok_emb.weight, act_emb.0.weight,
 dec_layers.N.*)."""
 from __future__ import annotations
 
-from math import inf, pi, prod
+from math import pi, prod
 from typing import Literal
 
 import torch
@@ -52,33 +52,28 @@ class DynamicsModel(nn.Module):
     @torch.no_grad()
     def generate(self, tokens: Tensor, act_id: Tensor, steps: int = 10,
                  which: Literal['linear', 'cosine', 'arccos'] = 'linear', temp: float = 1., topk: int = 50,
-                 masked_tok: int = 0) -> Tensor:
-        """MaskGIT iterative sampling — genie/dynamics.py:101-165. The transformer evaluations run on the B200
-        kernels; the per-step sampling bookkeeping (softmax / multinomial / top-k over h*w tokens) is host-side
-        torch plumbing exactly as in the reference."""
+                 masked_tok: int = 0, uniforms: Tensor | None = None) -> Tensor:
+        """MaskGIT iterative sampling of the next frame — genie/dynamics.py:101-165, as written there.
+
+        The reference packs the transformer input `[tokens, code]` once BEFORE its loop (lines 128-134) and never
+        refreshes it, so every iteration evaluates the model on the same input and only the multinomial draws differ
+        (`topk` is accepted and unused there, too). Here the transformer therefore runs ONCE, and all iterations —
+        softmax, draw, confidence, -inf on fixed positions, top-k, scatter — run in one fused launch
+        (ops.maskgit_sample). `uniforms` (steps, b*h*w) optionally injects the draws (parity tests); by default they
+        come from torch's CUDA generator. Returns pred_tok (b, t+1, h, w)."""
         b, t, h, w = tokens.shape
         schedule = self.get_schedule(steps, shape=(h, w), which=which)
-        mask = torch.ones(b, h, w, dtype=torch.bool, device=tokens.device)
-        code = torch.full((b, h, w), masked_tok, device=tokens.device, dtype=tokens.dtype)
+        code0 = torch.full((b, 1, h, w), masked_tok, device=tokens.device, dtype=tokens.dtype)
         mock = torch.zeros(b, 1, dtype=act_id.dtype, device=tokens.device)
-        act_all = torch.cat([act_id, mock], dim=1)
-        pred_tok = torch.cat([tokens, code[:, None]], dim=1)
-        for num_tokens in schedule.tolist():
-            if mask.sum() == 0:
-                break
-            tok_id = torch.cat([tokens, code[:, None]], dim=1)
-            _, logits = self(tok_id, act_all)
-            prob = torch.softmax(logits / temp, dim=-1).reshape(-1, logits.shape[-1])
-            pred = torch.multinomial(prob, num_samples=1)
-            conf = torch.gather(prob, -1, pred).reshape(b, h, w)
-            conf[~mask] = -inf
-            idxs = torch.topk(conf.view(b, -1), k=num_tokens, dim=-1).indices
-            pred = pred.view(b, -1)
-            code = code.view(b, -1).scatter(1, idxs, torch.gather(pred, -1, idxs).to(code.dtype)).view(b, h, w)
-            mask = mask.view(b, -1).scatter(1, idxs, False).view(b, h, w)
-            pred_tok = torch.cat([tokens, code[:, None]], dim=1)
-        assert mask.sum() == 0, f'Not all tokens were predicted. {mask.sum()} tokens left.'
-        return pred_tok
+        tok_id = torch.cat([tokens, code0], dim=1)
+        act_all = torch.cat([act_id.to(tokens.device), mock], dim=1)
+        logits_last = self._logits(tok_id, act_all)[:, -1]                        # (b, h, w, V) bf16
+        if uniforms is None:
+            uniforms = torch.rand((steps, b * h * w), device=tokens.device)
+        code, mask = ops.maskgit_sample(logits_last, uniforms, schedule, temp=temp, masked_tok=masked_tok)
+        left = int(mask.sum())
+        assert left == 0, f'Not all tokens were predicted. {left} tokens left.'
+        return torch.cat([tokens, code[:, None].to(tokens.dtype)], dim=1)
 
     def get_schedule(self, steps: int, shape: tuple[int, int],
                      which: Literal['linear', 'cosine', 'arccos'] = 'linear') -> Tensor:

@@ -9,9 +9,10 @@ import torch.nn as nn
 
 from ..utils import Blueprint, default, exists
 from .norm import AdaptiveGroupNorm, GroupNorm, SiLU
+from .image import BlurPooling2d
 from .video import CausalConv3d, DepthToSpaceTimeUpsample, SpaceTimeDownsample, VideoResidualBlock
 
-_OUT_OF_SCOPE = ('blur_pool', 'space_downsample', 'image-residual', 'causal-conv3d-transpose',
+_OUT_OF_SCOPE = ('space_downsample', 'image-residual', 'causal-conv3d-transpose',
                  'depth2space_upsample', 'depth2time_upsample', 'gelu', 'relu', 'leaky_relu')
 
 
@@ -26,6 +27,8 @@ def get_module(name: str):
         case 'space-time_attn':
             from .attention import SpaceTimeAttention
             return SpaceTimeAttention
+        case 'blur_pool':
+            return BlurPooling2d
         case 'video-residual':
             return VideoResidualBlock
         case 'causal-conv3d':

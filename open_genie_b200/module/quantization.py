@@ -41,6 +41,15 @@ class LookupFreeQuantization(nn.Module):
         codes = torch.arange(self.codebook_size, device=self.bit_mask.device)[:, None] & self.bit_mask
         return 2 * (codes != 0).float() - 1
 
+    def codes_from_indices(self, idxs: Tensor) -> Tensor:
+        """Token ids (b, t, h, w) -> the tensor `decode` expects, (b, C, t, h, w): bits (MSB first, `bit_mask`) -> +-1
+        codes -> proj_out. The inverse of the packing on quantization.py:98 followed by line 105; needed by the
+        inference roll-out (genie/genie.py:103 hands raw ids to decode, which cannot work)."""
+        bits = (idxs[..., None] & self.bit_mask.to(idxs.device)) != 0
+        codes = bits.to(torch.float32) * 2 - 1
+        out = self.proj_out(codes)
+        return out.movedim(-1, 1).contiguous()
+
     def forward(self, inp: Tensor, beta: float = 100., transpose: bool = False
                 ) -> Tuple[Tuple[Tensor, Tensor], Tensor | None]:
         # 'b d ... -> b ... d' is free for internal-format (NDHWC) tensors

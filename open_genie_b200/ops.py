@@ -972,6 +972,31 @@ def masked_cross_entropy(logits2d, target, mask):
     return _MaskedCeFn.apply(logits2d, target, mask)
 
 
+def maskgit_sample(logits_last: Tensor, uniforms: Tensor, schedule: Tensor, temp: float = 1.0, masked_tok: int = 0
+                   ) -> Tensor:
+    """All MaskGIT sampling iterations of DynamicsModel.generate (genie/dynamics.py:136-163) on the last frame's logits
+    (b, h, w, V): softmax -> CDF once (og_softmax_cdf), then one launch that runs every iteration (og_maskgit_sample).
+    uniforms: (steps, b*h*w) in [0, 1); schedule: (steps,) tokens to fix per iteration. Returns code (b, h, w) int64."""
+    _require_cuda(logits_last, 'logits')
+    b, h, w, V = logits_last.shape
+    P = h * w
+    lg = logits_last.detach()
+    if lg.dtype not in (bf16, f32) or not lg.is_contiguous():
+        lg = lg.float().contiguous()
+    dev = lg.device
+    s = _stream()
+    cdf = torch.empty((b * P, V), dtype=f32, device=dev)
+    _lib.call('og_softmax_cdf', lg.data_ptr(), int(lg.dtype == f32), b * P, V, 1.0 / float(temp), cdf.data_ptr(), s)
+    steps = int(schedule.numel())
+    u = uniforms.detach().to(device=dev, dtype=f32).reshape(steps, b * P).contiguous()
+    sch = schedule.detach().to(device=dev, dtype=torch.int32).contiguous()
+    code = torch.full((b, P), int(masked_tok), dtype=torch.int64, device=dev)
+    mask = torch.ones((b, P), dtype=torch.uint8, device=dev)
+    _lib.call('og_maskgit_sample', cdf.data_ptr(), u.data_ptr(), sch.data_ptr(), steps, b, P, V, code.data_ptr(),
+              mask.data_ptr(), s)
+    return code.view(b, h, w), mask.view(b, h, w)
+
+
 # ------------------------------------------------------------------------------------------------
 # fused VideoResidualBlock (no down-sampling): GN+SiLU -> conv -> GN+SiLU -> conv (+) 1x1x1 shortcut (+) add
 # ------------------------------------------------------------------------------------------------

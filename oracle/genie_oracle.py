@@ -435,3 +435,37 @@ def maskgit_schedule(steps: int, shape: Tuple[int, int], which: str = 'linear') 
     sch = ((s / s.sum()) * n).round().int().clamp(min=1)
     sch[-1] += n - sch.sum()
     return sch
+
+
+def inverse_cdf_draw(prob: Tensor, u: Tensor) -> Tensor:
+    """Stand-in for torch.multinomial(prob, 1) with INJECTED uniforms (the parity tests patch it into the reference's
+    loop too): index of the first element whose running sum exceeds u * total. prob (rows, V), u (rows,) -> (rows, 1)."""
+    cdf = prob.float().cumsum(-1)
+    tgt = (u.float() * cdf[:, -1])[:, None]
+    return (cdf <= tgt).sum(-1, keepdim=True).clamp_(max=prob.shape[-1] - 1)
+
+
+def maskgit_generate(logits_last: Tensor, tokens: Tensor, uniforms: Tensor, schedule: Tensor, temp: float = 1.,
+                     masked_tok: int = 0) -> Tensor:
+    """DynamicsModel.generate — dynamics.py:101-165, with the model evaluation factored out: the reference packs
+    tok_id = [tokens, code] ONCE before the loop (128) and never refreshes it (pred_tok on line 163 is only the return
+    value), so `self(tok_id, act_id)` (140) yields the same last-frame logits `logits_last` (b,h,w,V) every iteration.
+    uniforms (steps, b*h*w) replace torch.multinomial's internal randomness (145)."""
+    b, t, h, w = tokens.shape
+    mask = torch.ones(b, h, w, dtype=torch.bool)                        # 122
+    code = torch.full((b, h, w), masked_tok, dtype=tokens.dtype)        # 123
+    pred_tok = torch.cat([tokens, code[:, None]], dim=1)
+    for s, num_tokens in enumerate(schedule.tolist()):
+        if mask.sum() == 0:                                             # 137
+            break
+        prob = torch.softmax(logits_last / temp, dim=-1).reshape(-1, logits_last.shape[-1])     # 143-144
+        pred = inverse_cdf_draw(prob, uniforms[s])                      # 145
+        conf = torch.gather(prob, -1, pred).reshape(b, h, w)            # 146-147
+        conf[~mask] = -math.inf                                         # 151
+        idxs = torch.topk(conf.view(b, -1), k=num_tokens, dim=-1).indices   # 152
+        pred = pred.view(b, -1)
+        code = code.view(b, -1).scatter(1, idxs, torch.gather(pred, -1, idxs).to(code.dtype)).view(b, h, w)   # 158-159
+        mask = mask.view(b, -1).scatter(1, idxs, False).view(b, h, w)   # 160
+        pred_tok = torch.cat([tokens, code[:, None]], dim=1)            # 163
+    assert mask.sum() == 0
+    return pred_tok

@@ -248,9 +248,83 @@ def gen_action_dynamics():
                 'grads': summarize_grads(grads_of(dm))}, os.path.join(OUT, 'dynamics_mini.pt'))
 
 
+def gen_blur2d():
+    """BlurPooling2d (genie/module/image.py:43-85, registry name 'blur_pool'): outputs and input gradients."""
+    from genie.module.image import BlurPooling2d
+    x = O.det_uniform('kat.blur2d.x', (2, 16, 12, 12))
+    x.requires_grad_(True)
+    out = {}
+    for k, s in ((3, 2), (4, 2)):
+        m = BlurPooling2d(k, stride=s)
+        y = m(x)
+        y.backward(O.det_uniform(f'kat.blur2d.g.{k}', tuple(y.shape)))
+        out[f'k{k}s{s}'] = {'y': y.detach(), 'dx': x.grad.clone(), 'blur': m.blur.clone()}
+        x.grad = None
+    torch.save(out, os.path.join(OUT, 'blur2d.pt'))
+
+
+def gen_generate():
+    """DynamicsModel.generate run by the REAL reference with two test seams: torch.multinomial is replaced by the
+    inverse-CDF draw on injected uniforms (O.inverse_cdf_draw) and, for the big case, forward() returns given logits."""
+    out = {}
+    real_multinomial = torch.multinomial
+
+    def run(dm, tokens, act, steps, uniforms):
+        it = iter(uniforms)
+        torch.multinomial = lambda prob, num_samples=1, **kw: O.inverse_cdf_draw(prob, next(it))
+        try:
+            return dm.generate(tokens, act, steps=steps)
+        finally:
+            torch.multinomial = real_multinomial
+
+    # (1) the mini model end to end (P = 64 positions, V = 64)
+    dm = DynamicsModel(desc=fx.bp(fx.MINI_DYN_DESC), **fx.MINI_DYN)
+    load_det(dm)
+    b, t, h, w = 2, 3, 8, 8
+    u = O.det_uniform('gen.tokens', (b, t, h, w)) / (3 ** 0.5)
+    tokens = ((u + 1) * 0.5 * fx.MINI_DYN['tok_vocab']).long().clamp(0, fx.MINI_DYN['tok_vocab'] - 1)
+    ua = O.det_uniform('gen.act', (b, t)) / (3 ** 0.5)
+    act = ((ua + 1) * 0.5 * fx.MINI_DYN['act_vocab']).long().clamp(0, fx.MINI_DYN['act_vocab'] - 1)
+    steps = 5
+    uni = (O.det_uniform('gen.uniforms', (steps, b * h * w)) / (3 ** 0.5) + 1) * 0.5
+    with torch.no_grad():
+        tok_id = torch.cat([tokens, torch.zeros(b, 1, h, w, dtype=tokens.dtype)], 1)
+        act_id = torch.cat([act, torch.zeros(b, 1, dtype=act.dtype)], 1)
+        _, logits_last = dm(tok_id, act_id)
+    pred = run(dm, tokens, act, steps, uni)
+    sched = dm.get_schedule(steps, (h, w))
+    close(O.maskgit_generate(logits_last, tokens, uni, sched), pred, 'generate (mini model)')
+    out['mini'] = {'tokens': tokens, 'act': act, 'steps': steps, 'uniforms': uni, 'logits_last': logits_last,
+                   'pred_tok': pred}
+    # (2) configs[3] sizes: P = 256 positions, V = 1024, 25 steps (Genie.forward's steps_per_frame) on given logits
+    b, t, h, w, V, steps = 2, 2, 16, 16, 1024, 25
+    logits = O.det_uniform('gen.big.logits', (b, h, w, V), 2.0)
+    tokens = ((O.det_uniform('gen.big.tokens', (b, t, h, w)) / (3 ** 0.5) + 1) * 0.5 * V).long().clamp(0, V - 1)
+    act = torch.zeros(b, t, dtype=torch.long)
+    uni = (O.det_uniform('gen.big.uniforms', (steps, b * h * w)) / (3 ** 0.5) + 1) * 0.5
+    dm.forward = lambda tok_id, act_id: (None, logits)
+    for which in ('linear', 'cosine'):
+        it = iter(uni)
+        torch.multinomial = lambda prob, num_samples=1, **kw: O.inverse_cdf_draw(prob, next(it))
+        try:
+            pred = dm.generate(tokens, act, steps=steps, which=which)
+        finally:
+            torch.multinomial = real_multinomial
+        sched = dm.get_schedule(steps, (h, w), which)
+        close(O.maskgit_generate(logits, tokens, uni, sched), pred, f'generate (given logits, {which})')
+        out[f'big_{which}'] = {'tokens': tokens, 'steps': steps, 'pred_tok': pred}
+    torch.save(out, os.path.join(OUT, 'generate.pt'))
+
+
 if __name__ == '__main__':
+    if sys.argv[1:] == ['generate']:
+        with torch.no_grad():
+            gen_generate()
+        sys.exit(0)
     with torch.no_grad():
         gen_kats()
+        gen_generate()
+    gen_blur2d()
     gen_layers()
     gen_lfq()
     gen_st_block()

@@ -58,7 +58,7 @@ def test_dynamics_against_reference_golden(golden):
         assert abs(grads[k].norm().item() - n) / n < 0.1, (k, grads[k].norm().item(), n)
 
 
-def test_dynamics_generate_maskgit():
+def test_dynamics_generate_maskgit_shapes():
     import open_genie_b200 as og
     torch.manual_seed(0)
     dm = og.DynamicsModel(fx.MINI_DYN_DESC, **fx.MINI_DYN).to(DEV)
@@ -73,7 +73,10 @@ def test_dynamics_generate_maskgit():
 def test_genie_training_step_composition():
     import open_genie_b200 as og
     torch.manual_seed(0)
-    tok = og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=fx.MINI_D_CODEBOOK, gan_loss_weight=0,
+    # Genie needs token frames == action frames (tok_emb + act_emb broadcast, genie/dynamics.py:55): use the mini
+    # tokenizer blueprint without its temporal compression
+    no_time = lambda bp: tuple((n, {**kw, **({'time_factor': 1} if 'time_factor' in kw else {})}) for n, kw in bp)
+    tok = og.VideoTokenizer(no_time(fx.MINI_ENC), no_time(fx.MINI_DEC), d_codebook=fx.MINI_D_CODEBOOK, gan_loss_weight=0,
                             perc_loss_weight=0)
     gen = og.Genie(tok,
                    dict(enc_desc=fx.MINI_ACT_ENC, dec_desc=fx.MINI_ACT_DEC, d_codebook=4, n_embd=128, inp_shape=(32, 32)),

@@ -26,7 +26,8 @@ def test_parse_blueprint_expands_and_does_not_mutate():
 
 def test_registry_names():
     for name in ('space_attn', 'time_attn', 'space-time_attn', 'video-residual', 'causal-conv3d',
-                 'depth2spacetime_upsample', 'spacetime_downsample', 'group_norm', 'adaptive_group_norm', 'silu'):
+                 'depth2spacetime_upsample', 'spacetime_downsample', 'group_norm', 'adaptive_group_norm', 'silu',
+                 'blur_pool'):
         assert isinstance(get_module(name), type)
     with pytest.raises(ValueError, match='Unknown module name'):
         get_module('nope')
