@@ -93,6 +93,26 @@ int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw
 int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt, int kh,
                     int kw, int pt, int ph, int pw, int N, int T, int H, int W, og_stream_t stream);
 
+/* Strided CausalConv3d — SpaceTimeDownsample (genie/module/video.py:457-483) — as the SAME implicit GEMM, no im2col:
+ * geometry of video.py:154-164 (time padded at the FRONT only by pt = (kt-1) + (1-st); space symmetrically by
+ * ph = (kh-1)/2, pw = (kw-1)/2), output extents To = (T+pt-kt)/st+1, Ho = (H+2ph-kh)/sh+1, Wo likewise.
+ *   fwd  : the A box of a tap is a TMA box with element strides (st,sh,sw); OOB zero fill is the padding.
+ *   dgrad: input position i only receives taps == (i+pad) mod s, so the input grid splits into st*sh*sw residue
+ *          classes; each is a stride-1 implicit GEMM over dy with its tap subset, stored at stride s into dx
+ *          (st*sh*sw launches, no col2im, no atomics).
+ *   wgrad: dY boxes on the output grid, x boxes strided on the input grid; ACCUMULATES into dw.
+ * x / dx: bf16 [N,T,H,W,cin] (cin % 64 == 0); out: [N,To,Ho,Wo,cout]; dy: bf16 [N,To,Ho,Wo,cout] with cout % 64 == 0
+ * (zero padded by the caller; w_rows = real weight rows); w: packed bf16 [cout][ldw] as for og_conv3d_fwd. */
+int og_conv3d_strided_fwd(const void* x, int cin, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw,
+                          const void* w, int ldw, const float* bias, void* out, int out_f32, int N, int T, int H, int W,
+                          int cout, og_stream_t stream);
+int og_conv3d_strided_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int kt, int kh, int kw, int st,
+                            int sh, int sw, int pt, int ph, int pw, void* dx, int N, int T, int H, int W, int cin,
+                            og_stream_t stream);
+int og_conv3d_strided_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt, int kh,
+                            int kw, int st, int sh, int sw, int pt, int ph, int pw, int N, int T, int H, int W,
+                            og_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm / AdaptiveGroupNorm (+SiLU), NDHWC bf16, HBM-bound passes
  * Replaces F.group_norm / nn.GroupNorm + nn.SiLU (genie/module/video.py:607-608,622-623;
@@ -202,6 +222,13 @@ int og_sub_rows(const void* a, const void* b, void* out, int64_t n, og_stream_t 
  * segment of a packed [cout][ldw] weight matrix. src: fp32 or bf16. */
 int og_copy_rows_to_bf16(const void* src, int src_f32, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
                          int cols, og_stream_t stream);
+
+/* Data path (genie/module/data.py:181-234, Platformer2D.load_video_slice): decoded frames uint8 [N][T][H][W][3]
+ * as cv2.VideoCapture.read() returns them (bgr != 0) -> the colour swap of cvtColor(BGR2RGB), `/ 255.` and the
+ * 't h w c -> c t h w' rearrange in one pass on the device, so the host ships 1 byte per element instead of 4.
+ * out_kind 0: NCDHW fp32 [N,3,T,H,W]; out_kind 1: NDHWC bf16 with channel pitch cpad >= 3 (zero padded). */
+int og_frames_u8_to_video(const uint8_t* frames, int bgr, void* out, int out_kind, int cpad, int N, int T, int H, int W,
+                          og_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Lookup-Free Quantization (genie/module/quantization.py:77-133)

@@ -10,6 +10,7 @@ from .genie import Genie
 from .module import get_module, parse_blueprint
 from .optim import FusedAdamW
 from .ops import enable_zero_arena
+from .data import LightningDataset, LightningPlatformer2D, Platformer2D, VideoBatchPrefetcher, frames_to_video
 
 # LATENT_ACT_* blueprints: the intent of genie/__init__.py:10-54 in its HEAD-valid form: `n_embd`
 # dropped (SpaceTimeAttention does not accept it), heads 4 x 64 = 256 = n_embd, 'spacetime_upsample' (not in the
@@ -28,4 +29,5 @@ LATENT_ACT_DEC = (
 )
 
 __all__ = ['VideoTokenizer', 'LatentAction', 'DynamicsModel', 'Genie', 'LATENT_ACT_ENC', 'LATENT_ACT_DEC', 'MAGVIT2_ENC_DESC', 'MAGVIT2_DEC_DESC', 'REPR_TOK_ENC', 'REPR_TOK_DEC',
-           'get_module', 'parse_blueprint', 'FusedAdamW', 'enable_zero_arena']
+           'get_module', 'parse_blueprint', 'FusedAdamW', 'enable_zero_arena', 'LightningDataset', 'LightningPlatformer2D', 'Platformer2D',
+           'VideoBatchPrefetcher', 'frames_to_video']

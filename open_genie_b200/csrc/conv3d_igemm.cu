@@ -27,16 +27,26 @@
 namespace og {
 extern std::atomic<uint64_t> g_launches;
 
+// One K segment = a (sub)set of filter taps over one input tensor. Along every axis d the taps visited are
+// tap0[d] + j*tstep[d] (j < n[d]) of a (.., kh, kw) filter, and the A box of tap j is the M-tile box shifted by
+// sh0[d] + j*shstep[d]:
+//   forward                 n = k, tap0 = 0, tstep = 1, sh0 = -pad, shstep = +1      (x[v*stride + tap - pad])
+//   data gradient, stride 1 n = k, tap0 = 0, tstep = 1, sh0 = +pad, shstep = -1      (dy[v - (tap - pad)])
+//   data gradient, stride s one launch per residue class of the input position: n = #taps of that class,
+//                           tap0 = class, tstep = s, sh0 = e, shstep = -1            (see og_conv3d_strided_dgrad)
+// axis order: 0 = t, 1 = h, 2 = w.
 struct IgemmSeg {
   int cin_blocks;  // channels / 64
-  int kt, kh, kw;
-  int pt, ph, pw;
+  int n[3], tap0[3], tstep[3], sh0[3], shstep[3];
+  int kh, kw;      // filter extents (tap index = (it*kh + ih)*kw + iw)
 };
 
 struct IgemmParams {
   int nseg;
   IgemmSeg seg[2];
-  int sgn;         // +1: forward (x[v + tap - pad]); -1: data gradient (dy[v - (tap - pad)])
+  int sx[3];       // A box start = M-tile start * sx + shift (forward strided convolution: sx = stride; else 1)
+  int OT, OH, OW;  // extents of the OUTPUT tensor; M-tile voxel (t,h,w) is stored at (t*om[0]+oo[0], h*om[1]+oo[1], ...)
+  int om[3], oo[3];
   int b_mn_major;  // 0: B tile is [n rows][64 k] (K-major); 1: B tile is [k rows][n] in 64-wide panels (MN-major)
   int block_n;     // UMMA N (16..256)
   int num_n_tiles, num_m_tiles;
@@ -155,34 +165,38 @@ __global__ void __launch_bounds__(kThreads, 1)
         const TileCoord tc1 = decode_m_tile(p, m_super * p.m_sub + 1);  // second sub-tile (m_sub == 2)
         const int kb_begin = (int)(((long long)p.num_kb * split) / p.splits);
         const int kb_end = (int)(((long long)p.num_kb * (split + 1)) / p.splits);
-        // position (segment, tap = (it, ih, iw), channel block) of kb_begin: divisions once per work item,
+        // position (segment, tap = (jt, jh, jw), channel block) of kb_begin: divisions once per work item,
         // then the single producer thread only increments with carries (its instruction count per k-block
         // is what bounds the pipeline when MMAs are short)
-        const int nkb0 = p.seg[0].cin_blocks * p.seg[0].kt * p.seg[0].kh * p.seg[0].kw;
+        const int nkb0 = p.seg[0].cin_blocks * p.seg[0].n[0] * p.seg[0].n[1] * p.seg[0].n[2];
         int sidx = (kb_begin >= nkb0 && p.nseg > 1) ? 1 : 0;
         IgemmSeg sg = p.seg[sidx];
         int rel = kb_begin - (sidx ? nkb0 : 0);
-        int tap = rel / sg.cin_blocks;
-        int cb = rel - tap * sg.cin_blocks;
-        int it = tap / (sg.kh * sg.kw);
-        int ih = (tap / sg.kw) % sg.kh;
-        int iw = tap % sg.kw;
+        int tapc = rel / sg.cin_blocks;
+        int cb = rel - tapc * sg.cin_blocks;
+        int jt = tapc / (sg.n[1] * sg.n[2]);
+        int jh = (tapc / sg.n[2]) % sg.n[1];
+        int jw = tapc % sg.n[2];
+        const int aw0 = tc.w0 * p.sx[2], ah0 = tc.h0 * p.sx[1], at0 = tc.t0 * p.sx[0];
+        const int bw0 = tc1.w0 * p.sx[2], bh0 = tc1.h0 * p.sx[1], bt0 = tc1.t0 * p.sx[0];
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const CUtensorMap* mapA = (sidx == 0) ? &mapA0 : &mapA1;
-          const int dt = p.sgn * (it - sg.pt), dh = p.sgn * (ih - sg.ph), dw = p.sgn * (iw - sg.pw);
+          const int dt = sg.sh0[0] + jt * sg.shstep[0], dh = sg.sh0[1] + jh * sg.shstep[1],
+                    dw = sg.sh0[2] + jw * sg.shstep[2];
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           if (elect_one()) {
             mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-            tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, tc.w0 + dw, tc.h0 + dh, tc.t0 + dt, tc.n0);
+            tma_load_5d(sa, mapA, &full[stage], cb * kBlockK, aw0 + dw, ah0 + dh, at0 + dt, tc.n0);
             if (p.m_sub == 2)
-              tma_load_5d(sa + kABytes, mapA, &full[stage], cb * kBlockK, tc1.w0 + dw, tc1.h0 + dh, tc1.t0 + dt,
-                          tc1.n0);
+              tma_load_5d(sa + kABytes, mapA, &full[stage], cb * kBlockK, bw0 + dw, bh0 + dh, bt0 + dt, tc1.n0);
             if (!p.b_mn_major) {
               tma_load_2d(sb, &mapB, &full[stage], kb * kBlockK, n_tile * p.block_n);
             } else {
               // w[co][tap][ci] as (ci, tap, co): one (64 ci, 1 tap, 64 co) box per 64-wide N panel
+              const int tap = ((sg.tap0[0] + jt * sg.tstep[0]) * sg.kh + sg.tap0[1] + jh * sg.tstep[1]) * sg.kw +
+                              sg.tap0[2] + jw * sg.tstep[2];
               for (int pp = 0; pp < p.block_n / 64; ++pp)
                 tma_load_3d(sb + pp * (64 * 128), &mapB, &full[stage], n_tile * p.block_n + pp * 64, tap,
                             cb * kBlockK);
@@ -195,15 +209,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           if (++cb == sg.cin_blocks) {
             cb = 0;
-            ++tap;
-            if (++iw == sg.kw) {
-              iw = 0;
-              if (++ih == sg.kh) {
-                ih = 0;
-                if (++it == sg.kt) {  // next segment (the fused 1x1x1 shortcut)
+            if (++jw == sg.n[2]) {
+              jw = 0;
+              if (++jh == sg.n[1]) {
+                jh = 0;
+                if (++jt == sg.n[0]) {  // next segment (the fused 1x1x1 shortcut)
                   sidx = 1;
                   sg = p.seg[1];
-                  it = ih = iw = tap = 0;
+                  jt = jh = jw = 0;
                 }
               }
             }
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             const int dh = (r >> p.bw_log2) & ((1 << p.bh_log2) - 1);
             const int dt = (r >> (p.bw_log2 + p.bh_log2)) & ((1 << p.bt_log2) - 1);
             const int dn = r >> (p.bw_log2 + p.bh_log2 + p.bt_log2);
-            const long long vox = (((long long)(tc.n0 + dn) * p.T + tc.t0 + dt) * p.H + tc.h0 + dh) * p.W + tc.w0 + dw;
+            const long long vox = (((long long)(tc.n0 + dn) * p.OT + tc.t0 + dt) * p.OH + tc.h0 + dh) * p.OW + tc.w0 + dw;
             const uint4 u = *reinterpret_cast<const uint4*>(buf + j * 256 + (lane & 15) * 16);
             *reinterpret_cast<uint4*>(outp + vox * p.ldo + n_tile * 128 + (lane & 15) * 8) = u;
           }
@@ -351,7 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int dn = row >> (p.bw_log2 + p.bh_log2 + p.bt_log2);
       const int vn = tc.n0 + dn, vt = tc.t0 + dt, vh = tc.h0 + dh, vw = tc.w0 + dw;
       const bool row_ok = vn < p.N && vt < p.T && vh < p.H && vw < p.W;  // partial boxes: masked store
-      const long long vox = (((long long)vn * p.T + vt) * p.H + vh) * p.W + vw;
+      // (generalised store position: a strided data gradient writes one residue class of the input grid per launch)
+      const long long vox = (((long long)vn * p.OT + vt * p.om[0] + p.oo[0]) * p.OH + vh * p.om[1] + p.oo[1]) * p.OW +
+                            vw * p.om[2] + p.oo[2];
       const int col0 = n_tile * p.block_n;
 
       const uint32_t t_addr = tmem_base + acc * kAccStride + ms * p.block_n + ((uint32_t)(q * 32) << 16);
@@ -663,25 +678,76 @@ static int pick_block_n(int n_out, int num_m_tiles, bool mn_major) {
   return bn;
 }
 
-static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const IgemmSeg* segs, int nseg, int sgn,
-                        const void* w, int ldw, int k_off, int b_mn_major, int b_rows /*K rows for MN-major*/,
-                        int b_ntaps, const float* bias0, const float* bias1, const void* residual, void* out,
-                        int out_f32, int N, int T, int H, int W, int n_out, void* workspace, size_t workspace_bytes,
-                        double* gn_sums, const void* red_x, const float* red_A, const float* red_B, int red_act,
-                        float* red_S, cudaStream_t stream) {
+struct IgemmLaunch {
+  const void* a0 = nullptr;   // segment-0 input tensor (bf16 NDHWC), c0 channels, spatial extents aT x aH x aW
+  int c0 = 0;
+  int aT = 0, aH = 0, aW = 0;
+  int astride[3] = {1, 1, 1};  // element stride of the A boxes along (t, h, w): forward strided convolution
+  const void* a1 = nullptr;    // optional segment-1 tensor (the fused 1x1x1 shortcut), same extents as the output grid
+  int c1 = 0;
+  IgemmSeg segs[2];
+  int nseg = 1;
+  const void* w = nullptr;
+  int ldw = 0, k_off = 0, b_mn_major = 0, b_rows = 0, b_ntaps = 0;
+  const float* bias0 = nullptr;
+  const float* bias1 = nullptr;
+  const void* residual = nullptr;
+  void* out = nullptr;
+  int out_f32 = 0;
+  int N = 0, T = 0, H = 0, W = 0;  // the M grid (voxels this launch computes)
+  int OT = 0, OH = 0, OW = 0;      // output tensor extents (0 = same as the M grid)
+  int om[3] = {1, 1, 1}, oo[3] = {0, 0, 0};
+  int n_out = 0;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  double* gn_sums = nullptr;
+  const void* red_x = nullptr;
+  const float* red_A = nullptr;
+  const float* red_B = nullptr;
+  int red_act = 0;
+  float* red_S = nullptr;
+};
+
+static IgemmSeg make_seg(int cin_blocks, int kt, int kh, int kw, int pt, int ph, int pw, int sgn) {
+  IgemmSeg g;
+  g.cin_blocks = cin_blocks;
+  const int k[3] = {kt, kh, kw}, pd[3] = {pt, ph, pw};
+  for (int d = 0; d < 3; ++d) {
+    g.n[d] = k[d];
+    g.tap0[d] = 0;
+    g.tstep[d] = 1;
+    g.sh0[d] = -sgn * pd[d];
+    g.shstep[d] = sgn;
+  }
+  g.kh = kh;
+  g.kw = kw;
+  return g;
+}
+
+static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
+  const int N = L.N, T = L.T, H = L.H, W = L.W, n_out = L.n_out;
   OG_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0 && n_out > 0, "conv3d: empty problem");
+  const bool plain = (L.OT == 0) && L.astride[0] == 1 && L.astride[1] == 1 && L.astride[2] == 1;
   int bw, bh, bt, bn;
   choose_voxel_box(kBlockM, N, T, H, W, &bw, &bh, &bt, &bn);
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  p.nseg = nseg;
+  p.nseg = L.nseg;
   p.num_kb = 0;
-  for (int s = 0; s < nseg; ++s) {
-    p.seg[s] = segs[s];
-    p.num_kb += segs[s].cin_blocks * segs[s].kt * segs[s].kh * segs[s].kw;
+  for (int s = 0; s < L.nseg; ++s) {
+    p.seg[s] = L.segs[s];
+    p.num_kb += L.segs[s].cin_blocks * L.segs[s].n[0] * L.segs[s].n[1] * L.segs[s].n[2];
   }
-  p.sgn = sgn;
-  p.b_mn_major = b_mn_major;
+  OG_REQUIRE(p.num_kb > 0, "conv3d: empty reduction");
+  for (int d = 0; d < 3; ++d) {
+    p.sx[d] = L.astride[d];
+    p.om[d] = L.om[d];
+    p.oo[d] = L.oo[d];
+  }
+  p.OT = L.OT ? L.OT : T;
+  p.OH = L.OH ? L.OH : H;
+  p.OW = L.OW ? L.OW : W;
+  p.b_mn_major = L.b_mn_major;
   p.bw_log2 = ilog2(bw);
   p.bh_log2 = ilog2(bh);
   p.bt_log2 = ilog2(bt);
@@ -694,20 +760,20 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   p.H = H;
   p.W = W;
   p.num_m_tiles = ((N + bn - 1) / bn) * p.tiles_w * p.tiles_h * p.tiles_t;
-  p.block_n = pick_block_n(n_out, p.num_m_tiles, b_mn_major != 0);
+  p.block_n = pick_block_n(n_out, p.num_m_tiles, L.b_mn_major != 0);
   if (const char* e = getenv("OG_IGEMM_BN")) {  // tuning experiments only
     const int v = atoi(e);
-    if (v >= 16 && v <= 256 && (!b_mn_major || v >= 64)) p.block_n = v;
+    if (v >= 16 && v <= 256 && (!L.b_mn_major || v >= 64)) p.block_n = v;
   }
   p.num_n_tiles = (n_out + p.block_n - 1) / p.block_n;
   p.n_out = n_out;
   p.ldo = n_out;
-  p.out = out;
-  p.out_f32 = out_f32;
-  p.vec_ok = out_f32 ? (n_out % 4 == 0) : (n_out % 8 == 0);
-  p.bias0 = bias0;
-  p.bias1 = bias1;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = L.out;
+  p.out_f32 = L.out_f32;
+  p.vec_ok = L.out_f32 ? (n_out % 4 == 0) : (n_out % 8 == 0);
+  p.bias0 = L.bias0;
+  p.bias1 = L.bias1;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(L.residual);
   // TMA latency x smem capacity bounds the bytes/clk one SM can stream; sharing each B stage between two
   // 128-row M sub-tiles keeps the demand at (32+16) KB per 512 MMA-clk (same as a 128x256 tile).
   p.m_sub = (p.block_n <= 128 && p.num_m_tiles >= 2 * num_sms()) ? 2 : 1;
@@ -716,21 +782,21 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
     if ((v == 1 || v == 2) && v * p.block_n <= 256) p.m_sub = v;
   }
   const int stage_bytes = p.m_sub * kABytes + p.block_n * kBlockK * 2;
-  p.fast_store = (!out_f32 && n_out % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
+  p.fast_store = (!L.out_f32 && n_out % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
   // split-K when the tiles cannot fill the machine and each has a long K loop
   p.splits = 1;
   p.ws = nullptr;
-  {
+  if (plain) {
     const long long tiles = (long long)((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles;
     const size_t need = (size_t)N * T * H * W * n_out * sizeof(float);
-    if (tiles * 2 <= num_sms() && p.num_kb >= 32 && workspace && workspace_bytes >= need && !residual) {
+    if (tiles * 2 <= num_sms() && p.num_kb >= 32 && L.workspace && L.workspace_bytes >= need && !L.residual) {
       int sp = (int)(num_sms() / tiles);
       if (sp > p.num_kb / 8) sp = p.num_kb / 8;
       if (sp > 16) sp = 16;
       if (sp >= 2) {
         p.splits = sp;
-        p.ws = reinterpret_cast<float*>(workspace);
-        OG_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, stream));
+        p.ws = reinterpret_cast<float*>(L.workspace);
+        OG_CHECK_CUDA(cudaMemsetAsync(L.workspace, 0, need, stream));
       }
     }
   }
@@ -742,34 +808,42 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
 
   CUtensorMap mapA0, mapA1, mapB;
   {
-    uint64_t dims[5] = {(uint64_t)c0, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
-    uint64_t str[4] = {(uint64_t)c0 * 2, (uint64_t)W * c0 * 2, (uint64_t)H * W * c0 * 2, (uint64_t)T * H * W * c0 * 2};
-    uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, (uint32_t)bn};
-    int r = make_tmap_bf16(&mapA0, a0, 5, dims, str, box);
+    // forward strided convolution: the box spans bw*sw input positions and TMA traverses it with element stride sw,
+    // landing exactly the bw voxels the tile needs (the hardware zero-fills the out-of-range ones: the padding)
+    const int c0 = L.c0;
+    const int st = L.astride[0], sh = L.astride[1], sw = L.astride[2];
+    uint64_t dims[5] = {(uint64_t)c0, (uint64_t)L.aW, (uint64_t)L.aH, (uint64_t)L.aT, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)c0 * 2, (uint64_t)L.aW * c0 * 2, (uint64_t)L.aH * L.aW * c0 * 2,
+                       (uint64_t)L.aT * L.aH * L.aW * c0 * 2};
+    uint32_t box[5] = {kBlockK, (uint32_t)(bw * sw), (uint32_t)(bh * sh), (uint32_t)(bt * st), (uint32_t)bn};
+    uint32_t es[5] = {1, (uint32_t)sw, (uint32_t)sh, (uint32_t)st, 1};
+    OG_REQUIRE(box[1] <= 256 && box[2] <= 256 && box[3] <= 256, "conv3d: strided box exceeds the TMA limit");
+    int r = make_tmap_bf16(&mapA0, L.a0, 5, dims, str, box, es);
     if (r != OG_OK) return r;
   }
-  if (nseg > 1) {
+  if (L.nseg > 1) {
+    const int c1 = L.c1;
     uint64_t dims[5] = {(uint64_t)c1, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
     uint64_t str[4] = {(uint64_t)c1 * 2, (uint64_t)W * c1 * 2, (uint64_t)H * W * c1 * 2, (uint64_t)T * H * W * c1 * 2};
     uint32_t box[5] = {kBlockK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, (uint32_t)bn};
-    int r = make_tmap_bf16(&mapA1, a1, 5, dims, str, box);
+    int r = make_tmap_bf16(&mapA1, L.a1, 5, dims, str, box);
     if (r != OG_OK) return r;
   } else {
     mapA1 = mapA0;
   }
-  const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(w) + k_off;
-  if (!b_mn_major) {
+  const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(L.w) + L.k_off;
+  if (!L.b_mn_major) {
     // rows = output channels, contiguous k
     uint64_t ktot = (uint64_t)p.num_kb * kBlockK;
     uint64_t dims[2] = {ktot, (uint64_t)n_out};
-    uint64_t str[1] = {(uint64_t)ldw * 2};
+    uint64_t str[1] = {(uint64_t)L.ldw * 2};
     uint32_t box[2] = {kBlockK, (uint32_t)p.block_n};
     int r = make_tmap_bf16(&mapB, wb, 2, dims, str, box);
     if (r != OG_OK) return r;
   } else {
     // w[co][tap][ci] viewed as (ci, tap, co): a (64,1,64) box lands as one [64 co rows][64 ci] panel
-    uint64_t dims[3] = {(uint64_t)n_out, (uint64_t)b_ntaps, (uint64_t)b_rows};
-    uint64_t str[2] = {(uint64_t)n_out * 2, (uint64_t)ldw * 2};
+    uint64_t dims[3] = {(uint64_t)n_out, (uint64_t)L.b_ntaps, (uint64_t)L.b_rows};
+    uint64_t str[2] = {(uint64_t)n_out * 2, (uint64_t)L.ldw * 2};
     uint32_t box[3] = {64, 1, 64};
     int r = make_tmap_bf16(&mapB, wb, 3, dims, str, box);
     if (r != OG_OK) return r;
@@ -781,7 +855,7 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
     attr_set = true;
   }
   // operand swap for 128-wide Cout tiles (two voxel sub-tiles form the N = 256 operand): whole boxes only
-  p.swap = (p.block_n == 128 && p.m_sub == 2 && p.fast_store && p.splits == 1 && !residual && !red_S &&
+  p.swap = (plain && p.block_n == 128 && p.m_sub == 2 && p.fast_store && p.splits == 1 && !L.residual && !L.red_S &&
             n_out % 128 == 0 && (p.num_m_tiles % 2 == 0) && W % bw == 0 && H % bh == 0 && T % bt == 0 && N % bn == 0)
                ? 1 : 0;
   if (const char* e = getenv("OG_IGEMM_SWAP")) {
@@ -789,13 +863,13 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
   }
   // fused epilogue reductions need: staged bf16 stores, no split-K, every CTA tile inside one sample
   const int tiles_per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
-  const bool can_fuse = p.fast_store && p.splits == 1 && bn == 1 && (tiles_per_sample % p.m_sub == 0) && n_out <= 65536;
-  p.gn_sums = (gn_sums && can_fuse) ? gn_sums : nullptr;
-  p.red_S = (red_S && can_fuse) ? red_S : nullptr;
-  p.red_x = reinterpret_cast<const __nv_bfloat16*>(red_x);
-  p.red_A = red_A;
-  p.red_B = red_B;
-  p.red_act = red_act;
+  const bool can_fuse = plain && p.fast_store && p.splits == 1 && bn == 1 && (tiles_per_sample % p.m_sub == 0) && n_out <= 65536;
+  p.gn_sums = (L.gn_sums && can_fuse) ? L.gn_sums : nullptr;
+  p.red_S = (L.red_S && can_fuse) ? L.red_S : nullptr;
+  p.red_x = reinterpret_cast<const __nv_bfloat16*>(L.red_x);
+  p.red_A = L.red_A;
+  p.red_B = L.red_B;
+  p.red_act = L.red_act;
   const int total_tiles = ((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles * p.splits;
   int grid = num_sms();
   if (grid > total_tiles) grid = total_tiles;
@@ -806,19 +880,19 @@ static int launch_igemm(const void* a0, int c0, const void* a1, int c1, const Ig
     const long long total = (long long)N * T * H * W * n_out;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    og_splitk_finish_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p.ws, bias0, bias1, out, out_f32, n_out, total);
+    og_splitk_finish_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p.ws, L.bias0, L.bias1, L.out, L.out_f32, n_out, total);
     OG_CHECK_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
   }
   // requested reductions that could not be fused: run the stand-alone passes on the stored output
-  if (gn_sums && !p.gn_sums) {
-    OG_REQUIRE(!out_f32, "conv3d: GroupNorm statistics need a bf16 output");
-    int r = og_gn_stats(out, N, (int64_t)T * H * W, n_out, 1, gn_sums, (og_stream_t)stream);
+  if (L.gn_sums && !p.gn_sums) {
+    OG_REQUIRE(!L.out_f32 && plain, "conv3d: GroupNorm statistics need a plain bf16 output");
+    int r = og_gn_stats(L.out, N, (int64_t)T * H * W, n_out, 1, L.gn_sums, (og_stream_t)stream);
     if (r != OG_OK) return r;
   }
-  if (red_S && !p.red_S) {
-    OG_REQUIRE(!out_f32, "conv3d: fused backward reduction needs a bf16 output");
-    int r = og_affine_act_bwd_reduce(out, red_x, red_A, red_B, red_act, red_S, N, (int64_t)T * H * W, n_out,
+  if (L.red_S && !p.red_S) {
+    OG_REQUIRE(!L.out_f32 && plain, "conv3d: fused backward reduction needs a plain bf16 output");
+    int r = og_affine_act_bwd_reduce(L.out, L.red_x, L.red_A, L.red_B, L.red_act, L.red_S, N, (int64_t)T * H * W, n_out,
                                      (og_stream_t)stream);
     if (r != OG_OK) return r;
   }
@@ -839,12 +913,19 @@ extern "C" int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int
              "conv3d_fwd: bad kernel/padding (%d,%d,%d)/(%d,%d,%d)", kt, kh, kw, pt, ph, pw);
   const int ktot = kt * kh * kw * c0 + (x1 ? c1 : 0);
   OG_REQUIRE(ldw >= ktot && ldw % 8 == 0, "conv3d_fwd: ldw=%d must be >= %d and a multiple of 8", ldw, ktot);
-  IgemmSeg segs[2];
-  segs[0] = IgemmSeg{c0 / 64, kt, kh, kw, pt, ph, pw};
-  segs[1] = IgemmSeg{c1 / 64, 1, 1, 1, 0, 0, 0};
-  return launch_igemm(x0, c0, x1, c1, segs, x1 ? 2 : 1, +1, w, ldw, 0, 0, 0, 0, bias0, bias1, residual, out, out_f32, N, T,
-                      H, W, cout, workspace, workspace_bytes, gn_sums, nullptr, nullptr, nullptr, 0, nullptr,
-                      (cudaStream_t)stream);
+  IgemmLaunch L;
+  L.a0 = x0; L.c0 = c0; L.aT = T; L.aH = H; L.aW = W;
+  L.a1 = x1; L.c1 = c1;
+  L.segs[0] = make_seg(c0 / 64, kt, kh, kw, pt, ph, pw, +1);
+  L.segs[1] = make_seg(c1 / 64, 1, 1, 1, 0, 0, 0, +1);
+  L.nseg = x1 ? 2 : 1;
+  L.w = w; L.ldw = ldw;
+  L.bias0 = bias0; L.bias1 = bias1; L.residual = residual;
+  L.out = out; L.out_f32 = out_f32;
+  L.N = N; L.T = T; L.H = H; L.W = W; L.n_out = cout;
+  L.workspace = workspace; L.workspace_bytes = workspace_bytes;
+  L.gn_sums = gn_sums;
+  return launch_igemm(L, (cudaStream_t)stream);
 }
 
 extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int k_off, int kt, int kh,
@@ -858,9 +939,97 @@ extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void*
   OG_REQUIRE(cin > 0 && cin % 64 == 0, "conv3d_dgrad: cin=%d must be a multiple of 64", cin);
   OG_REQUIRE(k_off % 8 == 0 && ldw % 8 == 0, "conv3d_dgrad: k_off/ldw must be multiples of 8");
   OG_REQUIRE(w_rows > 0 && w_rows <= cout, "conv3d_dgrad: w_rows=%d must be in (0, cout]", w_rows);
-  IgemmSeg segs[1];
-  segs[0] = IgemmSeg{cout / 64, kt, kh, kw, pt, ph, pw};
-  return launch_igemm(dy, cout, nullptr, 0, segs, 1, -1, w, ldw, k_off, 1, w_rows, kt * kh * kw, nullptr, nullptr, nullptr, dx,
-                      dx_f32, N, T, H, W, cin, workspace, workspace_bytes, nullptr, red_x, red_A, red_B, red_act, red_S,
-                      (cudaStream_t)stream);
+  IgemmLaunch L;
+  L.a0 = dy; L.c0 = cout; L.aT = T; L.aH = H; L.aW = W;
+  L.segs[0] = make_seg(cout / 64, kt, kh, kw, pt, ph, pw, -1);
+  L.nseg = 1;
+  L.w = w; L.ldw = ldw; L.k_off = k_off; L.b_mn_major = 1; L.b_rows = w_rows; L.b_ntaps = kt * kh * kw;
+  L.out = dx; L.out_f32 = dx_f32;
+  L.N = N; L.T = T; L.H = H; L.W = W; L.n_out = cin;
+  L.workspace = workspace; L.workspace_bytes = workspace_bytes;
+  L.red_x = red_x; L.red_A = red_A; L.red_B = red_B; L.red_act = red_act; L.red_S = red_S;
+  return launch_igemm(L, (cudaStream_t)stream);
+}
+
+static int out_extent(int in, int pad_front, int pad_back, int k, int s) { return (in + pad_front + pad_back - k) / s + 1; }
+
+// Strided CausalConv3d forward (SpaceTimeDownsample, genie/module/video.py:457-483; geometry video.py:154-164: time is
+// padded at the FRONT only by pt = kt-1 + (1-st), space symmetrically by (k-1)//2), as the SAME implicit GEMM: the A
+// box of a tap is a strided TMA box (element strides = the convolution strides). No im2col buffer.
+extern "C" int og_conv3d_strided_fwd(const void* x, int cin, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph,
+                                     int pw, const void* w, int ldw, const float* bias, void* out, int out_f32, int N, int T,
+                                     int H, int W, int cout, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(x && w && out, "conv3d_strided_fwd: null pointer");
+  OG_REQUIRE(cin > 0 && cin % 64 == 0, "conv3d_strided_fwd: cin=%d must be a positive multiple of 64", cin);
+  OG_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && st >= 1 && sh >= 1 && sw >= 1 && st <= 8 && sh <= 8 && sw <= 8 && pt >= 0 &&
+                 ph >= 0 && pw >= 0, "conv3d_strided_fwd: bad kernel / stride / padding");
+  OG_REQUIRE(ldw >= kt * kh * kw * cin && ldw % 8 == 0, "conv3d_strided_fwd: bad ldw=%d", ldw);
+  const int To = out_extent(T, pt, 0, kt, st), Ho = out_extent(H, ph, ph, kh, sh), Wo = out_extent(W, pw, pw, kw, sw);
+  OG_REQUIRE(To >= 1 && Ho >= 1 && Wo >= 1, "conv3d_strided_fwd: empty output");
+  IgemmLaunch L;
+  L.a0 = x; L.c0 = cin; L.aT = T; L.aH = H; L.aW = W;
+  L.astride[0] = st; L.astride[1] = sh; L.astride[2] = sw;
+  L.segs[0] = make_seg(cin / 64, kt, kh, kw, pt, ph, pw, +1);
+  L.nseg = 1;
+  L.w = w; L.ldw = ldw;
+  L.bias0 = bias;
+  L.out = out; L.out_f32 = out_f32;
+  L.N = N; L.T = To; L.H = Ho; L.W = Wo; L.n_out = cout;
+  return launch_igemm(L, (cudaStream_t)stream);
+}
+
+// Data gradient of the strided convolution, without col2im: input position i receives dy[(i + pad - tap) / s] only from
+// the taps with tap == (i + pad) mod s, so the input grid splits into st*sh*sw residue classes, each of which is a
+// stride-1 implicit GEMM over dy with its own tap subset whose output rows are stored at stride s into dx.
+// dy: bf16 [N,To,Ho,Wo,cout] (cout % 64 == 0, zero padded by the caller; w_rows real rows); dx: bf16 [N,T,H,W,cin].
+extern "C" int og_conv3d_strided_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw, int kt, int kh, int kw,
+                                       int st, int sh, int sw, int pt, int ph, int pw, void* dx, int N, int T, int H, int W,
+                                       int cin, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(dy && w && dx, "conv3d_strided_dgrad: null pointer");
+  OG_REQUIRE(cout > 0 && cout % 64 == 0 && cin > 0 && cin % 64 == 0, "conv3d_strided_dgrad: channels must be multiples of 64");
+  OG_REQUIRE(w_rows > 0 && w_rows <= cout && ldw % 8 == 0, "conv3d_strided_dgrad: bad w_rows / ldw");
+  const int To = out_extent(T, pt, 0, kt, st), Ho = out_extent(H, ph, ph, kh, sh), Wo = out_extent(W, pw, pw, kw, sw);
+  OG_REQUIRE(To >= 1 && Ho >= 1 && Wo >= 1, "conv3d_strided_dgrad: empty output");
+  const int k[3] = {kt, kh, kw}, s[3] = {st, sh, sw}, pd[3] = {pt, ph, pw}, in[3] = {T, H, W};
+  bool any_empty = false;
+  for (int d = 0; d < 3; ++d)
+    if (k[d] < s[d]) any_empty = true;   // some residue classes have no tap: their rows of dx are zero
+  if (any_empty) OG_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)N * T * H * W * cin * 2, (cudaStream_t)stream));
+  for (int ct = 0; ct < st; ++ct)
+    for (int ch = 0; ch < sh; ++ch)
+      for (int cw = 0; cw < sw; ++cw) {
+        const int cls[3] = {ct, ch, cw};
+        IgemmLaunch L;
+        L.segs[0].cin_blocks = cout / 64;
+        L.segs[0].kh = kh;
+        L.segs[0].kw = kw;
+        int grid[3];
+        bool empty = false;
+        for (int d = 0; d < 3; ++d) {
+          // class c: input positions i with (i + pad) mod s == c, i.e. i = s*a + r, r = (c - pad) mod s (>= 0)
+          const int r = ((cls[d] - pd[d]) % s[d] + s[d]) % s[d];
+          const int ntap = cls[d] < k[d] ? (k[d] - 1 - cls[d]) / s[d] + 1 : 0;
+          grid[d] = in[d] > r ? (in[d] - r + s[d] - 1) / s[d] : 0;
+          if (ntap == 0 || grid[d] == 0) empty = true;
+          L.segs[0].n[d] = ntap;
+          L.segs[0].tap0[d] = cls[d];
+          L.segs[0].tstep[d] = s[d];
+          L.segs[0].sh0[d] = (r + pd[d] - cls[d]) / s[d];   // exact: r + pad - c is a multiple of s
+          L.segs[0].shstep[d] = -1;
+          L.om[d] = s[d];
+          L.oo[d] = r;
+        }
+        if (empty) continue;
+        L.a0 = dy; L.c0 = cout; L.aT = To; L.aH = Ho; L.aW = Wo;
+        L.nseg = 1;
+        L.w = w; L.ldw = ldw; L.b_mn_major = 1; L.b_rows = w_rows; L.b_ntaps = kt * kh * kw;
+        L.out = dx; L.out_f32 = 0;
+        L.N = N; L.T = grid[0]; L.H = grid[1]; L.W = grid[2]; L.n_out = cin;
+        L.OT = T; L.OH = H; L.OW = W;
+        int rc = launch_igemm(L, (cudaStream_t)stream);
+        if (rc != OG_OK) return rc;
+      }
+  return OG_OK;
 }

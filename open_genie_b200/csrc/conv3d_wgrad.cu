@@ -32,6 +32,7 @@ struct WgradParams {
   float* dw;
   long long ld_dw;
   int a_stages, b_stages;
+  int sx_t, sx_h, sx_w;  // X box start = dY box start * stride + tap offset (strided convolution; 1 otherwise)
   int vec_ok;  // dw rows 16-byte aligned: vector reductions
   int dbg;     // timing experiments only (OG_WGRAD_DBG): 1 = pretend A is K-major, 2 = pretend B is K-major, 4 = skip epilogue
 };
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
                 if (u < nt) {
                   for (int pp = 0; pp < panels; ++pp)
                     tma_load_5d(dst + u * tap_bytes + pp * kPanelBytes, &mapX, &full_b[sb], ci0 + pp * 64,
-                                w0 + off_w[j + u], h0 + off_h[j + u], t0 + off_t[j + u], n);
+                                w0 * p.sx_w + off_w[j + u], h0 * p.sx_h + off_h[j + u], t0 * p.sx_t + off_t[j + u], n);
                 }
               }
             }
@@ -257,20 +258,23 @@ __global__ void __launch_bounds__(kWThreads, 1)
 
 }  // namespace og
 
-extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt,
-                               int kh, int kw, int pt, int ph, int pw, int N, int T, int H, int W,
-                               og_stream_t stream) {
+// N,T,H,W: the dY grid (= output voxels). Ti,Hi,Wi / st,sh,sw: extents of x and the convolution strides.
+static int launch_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt, int kh, int kw,
+                        int pt, int ph, int pw, int N, int T, int H, int W, int Ti, int Hi, int Wi, int st, int sh, int sw,
+                        og_stream_t stream) {
   using namespace og;
   OG_REQUIRE(dy && x && dw, "conv3d_wgrad: null pointer");
   OG_REQUIRE(cin > 0 && cin % 64 == 0, "conv3d_wgrad: cin=%d must be a multiple of 64", cin);
   OG_REQUIRE(cout > 0 && cout % 8 == 0, "conv3d_wgrad: cout=%d must be a multiple of 8 (TMA row stride)", cout);
   OG_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && pt >= 0 && ph >= 0 && pw >= 0 && pt < kt && ph < kh && pw < kw,
              "conv3d_wgrad: bad kernel/padding");
+  OG_REQUIRE(st >= 1 && sh >= 1 && sw >= 1 && st <= 8 && sh <= 8 && sw <= 8, "conv3d_wgrad: bad stride");
   int bw, bh, bt, bn;
   choose_voxel_box(kVox, N, T, H, W, &bw, &bh, &bt, &bn);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.kt = kt; p.kh = kh; p.kw = kw; p.pt = pt; p.ph = ph; p.pw = pw;
+  p.sx_t = st; p.sx_h = sh; p.sx_w = sw;
   p.ntaps = kt * kh * kw;
   p.block_n = (cin % 128 == 0) ? 128 : 64;
   p.taps_per_group = 512 / p.block_n;
@@ -325,11 +329,14 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
     if (r != OG_OK) return r;
   }
   {
-    uint64_t dims[5] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
-    uint64_t str[4] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2,
-                       (uint64_t)T * H * W * cin * 2};
-    uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bt, (uint32_t)bn};
-    int r = make_tmap_bf16(&mapX, x, 5, dims, str, box);
+    // strided convolution: the x box spans bw*sw positions traversed with element stride sw (see conv3d_igemm.cu)
+    uint64_t dims[5] = {(uint64_t)cin, (uint64_t)Wi, (uint64_t)Hi, (uint64_t)Ti, (uint64_t)N};
+    uint64_t str[4] = {(uint64_t)cin * 2, (uint64_t)Wi * cin * 2, (uint64_t)Hi * Wi * cin * 2,
+                       (uint64_t)Ti * Hi * Wi * cin * 2};
+    uint32_t box[5] = {64, (uint32_t)(bw * sw), (uint32_t)(bh * sh), (uint32_t)(bt * st), (uint32_t)bn};
+    uint32_t es[5] = {1, (uint32_t)sw, (uint32_t)sh, (uint32_t)st, 1};
+    OG_REQUIRE(box[1] <= 256 && box[2] <= 256 && box[3] <= 256, "conv3d_wgrad: strided box exceeds the TMA limit");
+    int r = make_tmap_bf16(&mapX, x, 5, dims, str, box, es);
     if (r != OG_OK) return r;
   }
   static bool attr_set = false;
@@ -342,4 +349,23 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;
+}
+
+extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt,
+                               int kh, int kw, int pt, int ph, int pw, int N, int T, int H, int W,
+                               og_stream_t stream) {
+  return launch_wgrad(dy, cout, x, cin, dw, ld_dw, kt, kh, kw, pt, ph, pw, N, T, H, W, T, H, W, 1, 1, 1, stream);
+}
+
+// Weight gradient of the strided CausalConv3d (SpaceTimeDownsample): dy on the OUTPUT grid, x on the input grid
+// [N,T,H,W,cin]; x boxes are strided TMA boxes. Geometry as og_conv3d_strided_fwd.
+extern "C" int og_conv3d_strided_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt,
+                                       int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw, int N, int T, int H,
+                                       int W, og_stream_t stream) {
+  const int To = (T + pt - kt) / st + 1, Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+  if (To < 1 || Ho < 1 || Wo < 1) {
+    og::set_error("conv3d_strided_wgrad: empty output");
+    return OG_ERR_INVALID_ARGUMENT;
+  }
+  return launch_wgrad(dy, cout, x, cin, dw, ld_dw, kt, kh, kw, pt, ph, pw, N, To, Ho, Wo, T, H, W, st, sh, sw, stream);
 }

@@ -856,3 +856,53 @@ extern "C" int og_blurpool2d(const void* x, void* y, float* scratch, int backwar
   return blurpool_launch(x, y, scratch, backward, N, 1, H, W, cin, cout, 1, k, 1, sh, sw, 0, pad, stream);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// data path: decoded video frames -> model input
+// ------------------------------------------------------------------------------------------------
+namespace og {
+
+// frames: uint8 [N][T][H][W][3] exactly as OpenCV's VideoCapture.read() hands them over (BGR unless bgr == 0).
+// One thread per (n, t, h, w) pixel: the colour swap of cv2.cvtColor(BGR2RGB), the `/ 255.` and the
+// 't h w c -> c t h w' rearrange of Platformer2D.load_video_slice (genie/module/data.py:196-234) in one pass.
+//   out_kind 0: NCDHW fp32 (the reference's tensor format at every public method)
+//   out_kind 1: NDHWC bf16, channel pitch cpad >= 3, zero padded (the internal activation format)
+__global__ void og_frames_u8_to_video_kernel(const unsigned char* __restrict__ frames, int bgr, void* __restrict__ out,
+                                             int out_kind, int cpad, long long V, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const unsigned char* px = frames + i * 3;
+    const float c0 = (float)px[bgr ? 2 : 0] * (1.f / 255.f);
+    const float c1 = (float)px[1] * (1.f / 255.f);
+    const float c2 = (float)px[bgr ? 0 : 2] * (1.f / 255.f);
+    if (out_kind == 0) {
+      const long long n = i / V, v = i - n * V;
+      float* o = reinterpret_cast<float*>(out) + n * 3 * V + v;
+      o[0] = c0;
+      o[V] = c1;
+      o[2 * V] = c2;
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + i * cpad;
+      o[0] = __float2bfloat16_rn(c0);
+      o[1] = __float2bfloat16_rn(c1);
+      o[2] = __float2bfloat16_rn(c2);
+      for (int c = 3; c < cpad; ++c) o[c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+}  // namespace og
+
+extern "C" int og_frames_u8_to_video(const uint8_t* frames, int bgr, void* out, int out_kind, int cpad, int N, int T, int H,
+                                     int W, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(frames && out, "frames_u8_to_video: null pointer");
+  OG_REQUIRE(N > 0 && T > 0 && H > 0 && W > 0, "frames_u8_to_video: empty video");
+  OG_REQUIRE(out_kind == 0 || (out_kind == 1 && cpad >= 3), "frames_u8_to_video: bad output format");
+  const long long V = (long long)T * H * W, total = (long long)N * V;
+  og_frames_u8_to_video_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(frames, bgr, out, out_kind, cpad, V,
+                                                                                       total);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}

@@ -41,8 +41,10 @@ PFN_encodeTiled get_encode_tiled();
 
 // Encode a bf16 tensor map with 128-byte swizzle and zero OOB fill.
 // dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
+// elem_strides (optional): TMA traversal stride per dimension — box[i] then counts the SOURCE span, and
+// ceil(box[i] / elem_strides[i]) elements land in shared memory (strided convolution input boxes).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 int num_sms();
 

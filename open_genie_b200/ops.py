@@ -328,12 +328,15 @@ class ConvGeom:
         self.causal = causal
         self.ntaps = self.kt * self.kh * self.kw
         self.strided = stride != (1, 1, 1)
-        # implicit-GEMM kernel: stride 1, Cin multiple of 64; everything else goes through explicit im2col
+        # implicit-GEMM kernels: Cin multiple of 64 — stride 1 (`direct`) or strided (`strided_implicit`: strided TMA
+        # boxes forward / weight gradient, residue-class decomposition for the data gradient). Only Cin not in 64Z
+        # (the 3- and 18-channel stem convolutions) still goes through explicit im2col.
         self.direct = (not self.strided) and cin % 64 == 0
+        self.strided_implicit = self.strided and cin % 64 == 0 and causal and _os.environ.get('OG_STRIDED_IM2COL', '0') == '0'
         self.k_main = self.ntaps * cin
-        self.kpad = self.k_main if self.direct else _round_up(self.k_main, 64)
+        self.kpad = self.k_main if (self.direct or self.strided_implicit) else _round_up(self.k_main, 64)
         if not self.direct and not causal:
-            raise NotImplementedError('the im2col path implements CausalConv3d geometry only')
+            raise NotImplementedError('the strided / im2col paths implement CausalConv3d geometry only')
 
     def out_dims(self, T, H, W):
         if self.direct:
@@ -378,6 +381,12 @@ class _Conv3dFn(torch.autograd.Function):
                        'og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
                       _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), None, y.data_ptr(), int(out_f32),
                       B, T, H, W, geom.cout, ws.data_ptr(), ws.numel(), None, s)
+        elif geom.strided_implicit:
+            assert x2 is None
+            _conv_call('fwd', 2.0 * B * To * Ho * Wo * geom.cout * geom.k_main,
+                       'og_conv3d_strided_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.st, geom.sh, geom.sw,
+                       geom.pt, geom.ph, geom.pw, packed.data_ptr(), ldw, _ptr(bias), y.data_ptr(), int(out_f32), B, T, H,
+                       W, geom.cout, s)
         else:
             assert x2 is None
             col = torch.empty((B * To * Ho * Wo, geom.kpad), dtype=bf16, device=x.device)
@@ -391,7 +400,7 @@ class _Conv3dFn(torch.autograd.Function):
         ctx.in_shape = (B, C, T, H, W)
         ctx.has_bias = (bias is not None, bias2 is not None)
         ctx.w_shapes = (weight.shape, None if weight2 is None else weight2.shape)
-        ctx.save_for_backward(xi if geom.direct else col, x2i, packed)
+        ctx.save_for_backward(xi if (geom.direct or geom.strided_implicit) else col, x2i, packed)
         return y
 
     @staticmethod
@@ -440,6 +449,19 @@ class _Conv3dFn(torch.autograd.Function):
                 if need[4]:
                     g = wgrad(x2i, c1, 1, 1, 1, 0, 0, 0, ctx.w_shapes[1], (B, T, H, W))
                     dw2 = g.view(cout, 1, 1, 1, c1).permute(0, 4, 1, 2, 3)
+        elif geom.strided_implicit:
+            if need[0]:
+                dx = empty_internal(B, C, T, H, W, bf16, dev)
+                _conv_call('dgrad', 2.0 * B * To * Ho * Wo * cout * geom.k_main,
+                           'og_conv3d_strided_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, geom.kt, geom.kh,
+                           geom.kw, geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), B, T, H, W, C, s)
+            if need[1]:
+                rows = cpad if cpad != cout else cout
+                g = _zeros((rows, geom.ntaps * C), f32, dev)
+                _conv_call('wgrad', 2.0 * B * To * Ho * Wo * cout * geom.k_main,
+                           'og_conv3d_strided_wgrad', dyb.data_ptr(), cpad, xs.data_ptr(), C, g.data_ptr(), g.shape[1],
+                           geom.kt, geom.kh, geom.kw, geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, B, T, H, W, s)
+                dw = g[:cout].view(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
         else:
             col = xs
             if need[0]:

@@ -59,7 +59,44 @@ def test_causal_conv3d_matches_golden_and_oracle(golden):
     assert_close(grads['conv3d.bias'], b.grad, 2e-3, 1e-3 * b.grad.abs().max().item(), 'conv bias grad')
 
 
-def test_spacetime_downsample_im2col_path(golden):
+@pytest.mark.parametrize('cin,cout,stride,shape', [
+    (128, 128, (1, 2, 2), (2, 128, 4, 16, 16)),      # enc downsample #1 geometry (time stride 1)
+    (256, 256, (2, 2, 2), (2, 256, 4, 8, 8)),        # enc downsample #2/#3 geometry
+    (64, 192, (2, 2, 2), (1, 64, 5, 9, 7)),          # ragged extents: partial boxes, odd sizes, Cout != Cin
+    (64, 64, (1, 4, 4), (1, 64, 2, 16, 16)),         # stride 4 > kernel 3: residue classes without taps (zero rows of dx)
+])
+def test_strided_causal_conv_implicit_gemm(cin, cout, stride, shape):
+    """SpaceTimeDownsample as an IMPLICIT GEMM (strided TMA boxes forward / wgrad, residue-class data gradient):
+    forward, dx and dW against the oracle's F.pad + conv3d on identical bf16-rounded operands."""
+    from open_genie_b200.module.video import SpaceTimeDownsample
+    from open_genie_b200 import _lib
+    m = SpaceTimeDownsample(cin, 3, cout, time_factor=stride[0], space_factor=stride[1])
+    assert m.go_down.conv3d.geom.strided_implicit
+    sd = det_weights(m)
+    m.to(DEV)
+    m.go_down.out_f32 = True
+    x = bf16_round(O.det_uniform('strided.x', shape))
+    _lib.TIMING = []
+    try:
+        y, dx, grads = _run_layer(m, x)
+        names = {t[0] for t in _lib.TIMING}
+    finally:
+        _lib.TIMING = None
+    assert 'og_conv3d_strided_fwd' in names and 'og_conv3d_strided_dgrad' in names and 'og_conv3d_strided_wgrad' in names
+    assert not any('im2col' in n or 'col2im' in n for n in names)
+    sdr = round_conv_weights(sd)
+    xr = x.clone().requires_grad_(True)
+    w = sdr['go_down.conv3d.weight'].clone().requires_grad_(True)
+    yo = O.causal_conv3d(xr, w, sdr['go_down.conv3d.bias'], stride=stride)
+    assert y.shape == yo.shape
+    assert_close(y, yo, 1e-3, 1e-5 * yo.abs().max().item(), 'strided implicit fwd')
+    yo.backward(bf16_round((2.0 / yo.numel()) * y))
+    assert_close(dx, xr.grad, BF16_ULP, BF16_ULP * xr.grad.abs().max().item(), 'strided implicit dgrad')
+    assert_close(grads['go_down.conv3d.weight'], w.grad, 2e-3, 1e-3 * w.grad.abs().max().item(), 'strided implicit wgrad')
+
+
+def test_spacetime_downsample_im2col_path(golden, monkeypatch):
+    monkeypatch.setenv('OG_STRIDED_IM2COL', '1')        # the explicit path stays available for Cin not in 64Z
     from open_genie_b200.module.video import SpaceTimeDownsample
     g = golden('layers.pt')['spacetime_downsample']
     m = SpaceTimeDownsample(64, 3, 64, time_factor=2, space_factor=2)
