@@ -506,7 +506,13 @@ def main():
                 'sample': f'one training step ({dt:.1f} s): ' + cpu_sample_text(args.cpu_batch, threads, avail, kind)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing the process group down while a CUDA graph that captured NCCL collectives is still alive hung in
+        # ProcessGroupNCCL's destructor (2xB200, torch 2.11 / NCCL 2.28): finish all work, agree that everybody is done,
+        # then leave without running the destructors.
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -131,7 +131,9 @@ int og_gn_finalize(const double* sums, int N, int C, int G, int64_t V, float eps
                    const float* beta, const float* cond_scale, const float* cond_shift, float* A, float* B,
                    float* mean_rstd, og_stream_t stream);
 
-/* y = act(x*A + B); act: 0 = identity, 1 = SiLU. x,y: bf16 [N,V,C]. */
+/* y = act(x*A + B); act: 0 = identity, 1 = SiLU, 2 = LeakyReLU(0.01) (the discriminators' nn.LeakyReLU(),
+ * genie/module/image.py:124-137), 3 = ReLU (VGG16 of the perceptual loss). x,y: bf16 [N,V,C]. The same codes are
+ * accepted by every `act` argument below. */
 int og_affine_act_fwd(const void* x, const float* A, const float* B, void* y, int N, int64_t V, int C, int act,
                       og_stream_t stream);
 
@@ -208,6 +210,13 @@ int og_mse_fwd(const float* rec_ndhwc, const float* tgt_ncdhw, int N, int C, int
                og_stream_t stream);
 int og_mse_bwd(const float* rec_ndhwc, const float* tgt_ncdhw, const float* gscale, int N, int C, int cpad,
                int64_t V, void* drec, og_stream_t stream);
+
+/* Perceptual-loss pieces that are not convolutions (genie/module/loss.py:34-107, torchvision vgg16.features):
+ * nn.MaxPool2d(2, 2) on NHWC bf16 (C % 8 == 0), and out[0] += sum (a - b)^2 over n bf16 elements (n % 8 == 0) — the
+ * feature-space mse_loss numerator (loss.py:100-103). The VGG convolutions / ReLUs run on og_conv3d_fwd (kt = 1) and
+ * og_affine_act_fwd (act = 3). */
+int og_maxpool2x2(const void* x, void* y, int N, int H, int W, int C, og_stream_t stream);
+int og_sqdiff_sum(const void* a, const void* b, int64_t n, float* out, og_stream_t stream);
 
 /* out[c] += sum_rows x[row][c] (conv bias gradient). x: bf16 [rows][ld]. */
 int og_colsum(const void* x, int64_t rows, int C, int ld, float* out, og_stream_t stream);

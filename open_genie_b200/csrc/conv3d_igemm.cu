@@ -474,10 +474,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float xv = q2 ? xf.y : xf.x;
                     const uint32_t raw = idx < 32 ? v0[idx] : v1[idx - 32];
                     float dv = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw)));  // what bwd_apply will read
-                    if (p.red_act) {
+                    if (p.red_act == 1) {
                       const float pre = fmaf(xv, coef_s[c + idx], coef_s[256 + c + idx]);
                       const float sg = 1.f / (1.f + __expf(-pre));
                       dv *= sg * (1.f + pre * (1.f - sg));
+                    } else if (p.red_act >= 2) {  // LeakyReLU(0.01) / ReLU (act codes of norm_act.cu)
+                      const float pre = fmaf(xv, coef_s[c + idx], coef_s[256 + c + idx]);
+                      if (pre <= 0.f) dv *= (p.red_act == 2 ? 0.01f : 0.f);
                     }
                     if (!row_ok) dv = 0.f;
                     d1[idx] = dv;

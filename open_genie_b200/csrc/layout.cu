@@ -906,3 +906,78 @@ extern "C" int og_frames_u8_to_video(const uint8_t* frames, int bgr, void* out, 
   g_launches.fetch_add(1);
   return OG_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// perceptual loss helpers (genie/module/loss.py:34-107): VGG16 feature extractor pieces that are not conv / ReLU
+// ------------------------------------------------------------------------------------------------
+namespace og {
+
+// nn.MaxPool2d(kernel_size=2, stride=2) on NHWC bf16 (torchvision vgg16.features.{4,9,16,23}); H, W even or floor.
+__global__ void og_maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int Ho, int Wo, int cv,
+                                     long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long n = r / Ho;
+    const long long base = ((n * H + 2 * ho) * W + 2 * wo) * cv + c;
+    const uint4 q[4] = {__ldg(x + base), __ldg(x + base + cv), __ldg(x + base + (long long)W * cv),
+                        __ldg(x + base + (long long)W * cv + cv)};
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 m = reinterpret_cast<const __nv_bfloat162*>(&q[0])[e];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) m = __hmax2(m, reinterpret_cast<const __nv_bfloat162*>(&q[k])[e]);
+      oh[e] = m;
+    }
+    y[i] = o;
+  }
+}
+
+// out[0] += sum (a - b)^2 over n bf16 elements (n % 8 == 0): the feature-space mse of the perceptual loss
+__global__ void og_sqdiff_sum_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, long long nvec,
+                                     float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 ua = __ldg(a + i), ub = __ldg(b + i);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+      const float d0 = fa.x - fb.x, d1 = fa.y - fb.y;
+      acc = fmaf(d0, d0, fmaf(d1, d1, acc));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+}  // namespace og
+
+extern "C" int og_maxpool2x2(const void* x, void* y, int N, int H, int W, int C, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(x && y && N > 0 && H >= 2 && W >= 2, "maxpool2x2: bad arguments");
+  OG_REQUIRE(C % 8 == 0, "maxpool2x2: C=%d must be a multiple of 8", C);
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  og_maxpool2x2_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, H, W, Ho, Wo, C / 8,
+                                                                               total);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_sqdiff_sum(const void* a, const void* b, int64_t n, float* out, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(a && b && out && n > 0 && n % 8 == 0, "sqdiff_sum: bad arguments (n %% 8 == 0)");
+  og_sqdiff_sum_kernel<<<ew_blocks(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, n / 8, out);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}

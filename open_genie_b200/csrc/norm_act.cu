@@ -48,6 +48,24 @@ __device__ __forceinline__ float silu_grad_f(float x) {
   return s * fmaf(x, 1.f - s, 1.f);
 }
 
+// Activation codes shared by every pass: 0 identity, 1 SiLU, 2 LeakyReLU(0.01) (nn.LeakyReLU() of the discriminators,
+// genie/module/image.py:124-137, discriminator.py:97), 3 ReLU (VGG16 features of the perceptual loss, loss.py:46).
+// SiLU passes work on h = pre/2 (coefficients pre-halved by the caller, see above); the others on pre itself.
+static constexpr float kLeakySlope = 0.01f;
+__device__ __forceinline__ float act_fwd_val(float v, int act) {   // v = h for SiLU, pre otherwise
+  if (act == 1) return silu_from_half(v);
+  if (act == 2) return v > 0.f ? v : kLeakySlope * v;
+  if (act == 3) return fmaxf(v, 0.f);
+  return v;
+}
+// e such that dpre = e * (act == 1 ? 1/2 : 1): SiLU returns 2*dpre (its callers fold the 1/2 into the coefficients)
+__device__ __forceinline__ float act_bwd_e(float d, float v, int act) {
+  if (act == 1) return fmaf(d, silu_grad2_from_half(v), d);
+  if (act == 2) return v > 0.f ? d : kLeakySlope * d;
+  if (act == 3) return v > 0.f ? d : 0.f;
+  return d;
+}
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -197,7 +215,7 @@ __global__ void __launch_bounds__(256) og_affine_act_fwd_kernel(const uint4* __r
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float pre = fmaf(f[k], av[k], bv[k]);
-      f[k] = act ? silu_f(pre) : pre;
+      f[k] = act == 1 ? silu_f(pre) : act_fwd_val(pre, act);
     }
     y[i] = pack8(f);
   }
@@ -221,7 +239,7 @@ __global__ void __launch_bounds__(256, 3)
   if (rl < lanes && r_begin < V) {
     // act: h = pre/2 = x*(A/2) + B/2 and e = dy (1 + w) = 2 dpre (see silu_grad2_from_half); sums halved at the end
     float av[8], bv[8];
-    const float cs = act ? 0.5f : 1.f;
+    const float cs = act == 1 ? 0.5f : 1.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       av[k] = cs * A[(long long)n * C + cv * 8 + k];
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(256, 3)
       unpack8(udv, fd);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float e = act ? fmaf(fd[k], silu_grad2_from_half(fmaf(fx[k], av[k], bv[k])), fd[k]) : fd[k];
+        const float e = act ? act_bwd_e(fd[k], fmaf(fx[k], av[k], bv[k]), act) : fd[k];
         s1[k] += e;
         s2[k] = fmaf(e, fx[k], s2[k]);
       }
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float a = __ldg(A + o + k), b = __ldg(B + o + k);
-      const float dpre = act ? fd[k] * silu_grad_f(fmaf(fx[k], a, b)) : fd[k];
+      const float dpre = act == 1 ? fd[k] * silu_grad_f(fmaf(fx[k], a, b)) : act_bwd_e(fd[k], fmaf(fx[k], a, b), act);
       float v = a * dpre;
       if (Q) v += __ldg(Q + o + k) * fx[k] + __ldg(R + o + k);
       if (add) v += fa[k];
@@ -405,7 +423,7 @@ __global__ void __launch_bounds__(256, 4)
       }
     }
   }
-  if (act) {
+  if (act == 1) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       av[k] *= 0.5f;
@@ -425,7 +443,7 @@ __global__ void __launch_bounds__(256, 4)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float h = fmaf(f[k], av[k], bv[k]);
-        f[k] = act ? silu_from_half(h) : h;
+        f[k] = act_fwd_val(h, act);
       }
       y[base + (r + (long long)j * lanes) * cvs] = pack8(f);
     }
@@ -436,7 +454,7 @@ __global__ void __launch_bounds__(256, 4)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float h = fmaf(f[k], av[k], bv[k]);
-      f[k] = act ? silu_from_half(h) : h;
+      f[k] = act_fwd_val(h, act);
     }
     y[base + r * cvs] = pack8(f);
   }
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(256, 3)
       av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
       bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
     }
-    if (act) {  // h = pre/2 and e = 2 dpre below: fold both halves into the coefficients
+    if (act == 1) {  // h = pre/2 and e = 2 dpre below: fold both halves into the coefficients
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         av[k] *= 0.5f;
@@ -542,7 +560,7 @@ __global__ void __launch_bounds__(256, 3)
       if (add) unpack8(ua, fa);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float e = act ? fmaf(fd[k], silu_grad2_from_half(fmaf(fx[k], av[k], bv[k])), fd[k]) : fd[k];
+        const float e = act ? act_bwd_e(fd[k], fmaf(fx[k], av[k], bv[k]), act) : fd[k];
         float v = fmaf(av[k], e, fmaf(qv[k], fx[k], rv[k]));
         if (add) v += fa[k];
         out[k] = v;

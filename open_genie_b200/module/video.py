@@ -79,7 +79,7 @@ class Conv3dParams(nn.Module):
             ld = self.geom.kpad + (e.in_channels if e is not None else 0)
             if self._packed is None or self._packed.shape[1] != ld or self._packed.device != w.device:
                 self._packed = torch.zeros((self.out_channels, ld), dtype=torch.bfloat16, device=w.device)
-            ops.pack_weight(w, self._packed, 0)
+            ops.pack_weight(w, self._packed, 0, self.geom.cin_pad)
             if e is not None:
                 ops.pack_weight(e.weight, self._packed, self.geom.kpad)
             self._packed_key = key
@@ -92,6 +92,8 @@ class Conv3dParams(nn.Module):
         owner = self._fused_into() if self._fused_into is not None else None
         if owner is not None:
             return owner.packed(), owner.geom.kpad
+        if self.geom.padded:     # every tap's Cin channels sit at a pitch of cin_pad in the packed operand
+            return self.packed(), 0, self.in_channels, self.geom.cin_pad
         return self.packed(), 0
 
     def forward(self, x: Tensor, x2: Tensor | None = None, out_f32: bool = False) -> Tensor:

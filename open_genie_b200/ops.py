@@ -328,15 +328,21 @@ class ConvGeom:
         self.causal = causal
         self.ntaps = self.kt * self.kh * self.kw
         self.strided = stride != (1, 1, 1)
-        # implicit-GEMM kernels: Cin multiple of 64 — stride 1 (`direct`) or strided (`strided_implicit`: strided TMA
-        # boxes forward / weight gradient, residue-class decomposition for the data gradient). Only Cin not in 64Z
-        # (the 3- and 18-channel stem convolutions) still goes through explicit im2col.
-        self.direct = (not self.strided) and cin % 64 == 0
-        self.strided_implicit = self.strided and cin % 64 == 0 and causal and _os.environ.get('OG_STRIDED_IM2COL', '0') == '0'
-        self.k_main = self.ntaps * cin
-        self.kpad = self.k_main if (self.direct or self.strided_implicit) else _round_up(self.k_main, 64)
-        if not self.direct and not causal:
-            raise NotImplementedError('the strided / im2col paths implement CausalConv3d geometry only')
+        # Every convolution is an implicit GEMM: stride 1 (`direct`) or strided (`strided_implicit`: strided TMA boxes
+        # forward / weight gradient, residue-class decomposition for the data gradient). A k-block of the kernels is 64
+        # channels of one tap, so an input with Cin not in 64Z (the 3- and 18-channel stem convolutions) is zero-padded
+        # to `cin_pad` channels (a pass over a 3-channel tensor) and its packed weights likewise — for Cin = 3 that costs
+        # ~0.3 ms of extra tensor-core time per training step and replaces a 134 MB im2col buffer + its two passes.
+        # OG_STRIDED_IM2COL=1 keeps the explicit im2col + GEMM form of round 1 for strided / narrow layers (tests).
+        legacy = _os.environ.get('OG_STRIDED_IM2COL', '0') != '0' and causal and (self.strided or cin % 64 != 0)
+        self.cin_pad = cin if legacy else _round_up(cin, 64)
+        self.padded = self.cin_pad != cin
+        self.direct = (not self.strided) and not legacy
+        self.strided_implicit = self.strided and causal and not legacy
+        self.k_main = self.ntaps * cin                      # algorithmic reduction length (FLOP accounting)
+        self.kpad = self.ntaps * self.cin_pad if (self.direct or self.strided_implicit) else _round_up(self.k_main, 64)
+        if self.strided and not causal:
+            raise NotImplementedError('strided convolutions implement CausalConv3d geometry only')
 
     def out_dims(self, T, H, W):
         if self.direct:
@@ -345,46 +351,68 @@ class ConvGeom:
                 (W + 2 * self.pw - self.kw) // self.sw + 1)
 
 
-def pack_weight(weight: Tensor, dst: Tensor, col_off: int):
+def pack_weight(weight: Tensor, dst: Tensor, col_off: int, cin_pad: int = 0):
     """fp32 (Cout,Cin,kt,kh,kw) parameter (channels_last_3d memory = [Cout][tap][Cin]) -> bf16 segment of the
-    packed operand matrix dst[Cout][ld] starting at column col_off."""
+    packed operand matrix dst[Cout][ld] starting at column col_off. With cin_pad > Cin every tap's Cin channels land at
+    a pitch of cin_pad (the pad columns of `dst` stay zero): dst must then be exactly [Cout][ntaps*cin_pad]."""
     w = weight.detach()
-    cout = w.shape[0]
+    cout, cin = w.shape[0], w.shape[1]
     k = w.numel() // cout
     if not w.permute(0, 2, 3, 4, 1).is_contiguous():
         w = w.permute(0, 2, 3, 4, 1).contiguous()
+    if cin_pad and cin_pad != cin:
+        assert col_off == 0 and dst.shape[1] == (k // cin) * cin_pad
+        _lib.call('og_copy_rows_to_bf16', w.data_ptr(), 1, cin, dst.data_ptr(), cin_pad, cout * (k // cin), cin, _stream())
+        return
     _lib.call('og_copy_rows_to_bf16', w.data_ptr(), 1, k, dst.data_ptr() + 2 * col_off, dst.shape[1], cout, k, _stream())
+
+
+def _pad_input_channels(xi: Tensor, cpad: int) -> Tensor:
+    """internal bf16 (B,C,T,H,W) -> (B,cpad,T,H,W) with zero channels appended (narrow-Cin stem convolutions)."""
+    B, C, T, H, W = xi.shape
+    y = empty_internal(B, cpad, T, H, W, bf16, xi.device)
+    _lib.call('og_pad_channels', xi.data_ptr(), 0, y.data_ptr(), B * T * H * W, C, cpad, _stream())
+    return y
 
 
 class _Conv3dFn(torch.autograd.Function):
     """y = conv(x; w, b) [+ conv1x1(x2; w2, b2)]   — og_conv3d_fwd / dgrad / wgrad, or im2col + the same kernels."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, x2, weight2, bias2, packed, geom: ConvGeom, out_f32: bool):
+    def forward(ctx, x, weight, bias, x2, weight2, bias2, packed, geom: ConvGeom, out_f32: bool, residual=None):
         _require_cuda(x, 'conv input')
         B, C, T, H, W = x.shape
         assert C == geom.cin, f'conv: expected {geom.cin} input channels, got {C}'
         s = _stream()
         xi = to_internal(x, bf16)
+        if geom.padded:
+            assert x2 is None, 'a narrow-Cin convolution cannot carry a fused shortcut'
+            xi = _pad_input_channels(xi, geom.cin_pad)
+        Cp = geom.cin_pad                      # channel count the kernels see
         To, Ho, Wo = geom.out_dims(T, H, W)
         y = empty_internal(B, geom.cout, To, Ho, Wo, f32 if out_f32 else bf16, x.device)
         ldw = packed.shape[1]
         ws = _workspace(x.device, B * To * Ho * Wo * geom.cout * 4)
         x2i = None
         col = None
+        resi = None
+        if residual is not None:     # out = conv(x) + residual, added in fp32 inside the GEMM epilogue (stride-1 convs)
+            assert geom.direct and not out_f32, 'the fused residual add needs a stride-1 convolution with a bf16 output'
+            resi = to_internal(residual, bf16)
+            assert tuple(resi.shape) == (B, geom.cout, To, Ho, Wo), 'residual must have the shape of the output'
         if geom.direct:
             c1 = 0
             if x2 is not None:
                 x2i = to_internal(x2, bf16)
                 c1 = x2i.shape[1]
             _conv_call('fwd', 2.0 * B * T * H * W * geom.cout * (geom.k_main + c1),
-                       'og_conv3d_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
-                      _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), None, y.data_ptr(), int(out_f32),
+                       'og_conv3d_fwd', xi.data_ptr(), Cp, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw,
+                      _ptr(x2i), c1, packed.data_ptr(), ldw, _ptr(bias), _ptr(bias2), _ptr(resi), y.data_ptr(), int(out_f32),
                       B, T, H, W, geom.cout, ws.data_ptr(), ws.numel(), None, s)
         elif geom.strided_implicit:
             assert x2 is None
             _conv_call('fwd', 2.0 * B * To * Ho * Wo * geom.cout * geom.k_main,
-                       'og_conv3d_strided_fwd', xi.data_ptr(), C, geom.kt, geom.kh, geom.kw, geom.st, geom.sh, geom.sw,
+                       'og_conv3d_strided_fwd', xi.data_ptr(), Cp, geom.kt, geom.kh, geom.kw, geom.st, geom.sh, geom.sw,
                        geom.pt, geom.ph, geom.pw, packed.data_ptr(), ldw, _ptr(bias), y.data_ptr(), int(out_f32), B, T, H,
                        W, geom.cout, s)
         else:
@@ -399,6 +427,7 @@ class _Conv3dFn(torch.autograd.Function):
         ctx.geom = geom
         ctx.in_shape = (B, C, T, H, W)
         ctx.has_bias = (bias is not None, bias2 is not None)
+        ctx.has_residual = residual is not None
         ctx.w_shapes = (weight.shape, None if weight2 is None else weight2.shape)
         ctx.save_for_backward(xi if (geom.direct or geom.strided_implicit) else col, x2i, packed)
         return y
@@ -423,21 +452,25 @@ class _Conv3dFn(torch.autograd.Function):
             """fp32 gradient with the parameter's channels_last_3d memory: [cout][tap][cin]."""
             rows = cpad if cpad != cout else cout
             g = _zeros((rows, kt * kh * kw * cin), f32, dev)
-            _conv_call('wgrad', 2.0 * dims[0] * dims[1] * dims[2] * dims[3] * cout * min(cin, geom.k_main) * kt * kh * kw,
+            real_cin = C if (geom.padded and cin == geom.cin_pad) else cin      # algorithmic FLOPs: no padding counted
+            _conv_call('wgrad', 2.0 * dims[0] * dims[1] * dims[2] * dims[3] * cout * min(real_cin, geom.k_main) * kt * kh * kw,
                        'og_conv3d_wgrad', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(), g.shape[1],
                       kt, kh, kw, pt, ph, pw, dims[0], dims[1], dims[2], dims[3], s)
             return g[:cout]
 
+        Cp = geom.cin_pad
         if geom.direct:
             if need[0]:
-                dx = empty_internal(B, C, T, H, W, bf16, dev)
+                dx = empty_internal(B, Cp, T, H, W, bf16, dev)
                 _conv_call('dgrad', 2.0 * B * T * H * W * cout * geom.k_main,
                            'og_conv3d_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, 0, geom.kt, geom.kh,
-                           geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, C, ws.data_ptr(), ws.numel(),
+                           geom.kw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), 0, B, T, H, W, Cp, ws.data_ptr(), ws.numel(),
                            None, None, None, 0, None, s)
+                if geom.padded:
+                    dx = dx[:, :C]
             if need[1]:
-                g = wgrad(xs, C, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, ctx.w_shapes[0], (B, T, H, W))
-                dw = g.view(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
+                g = wgrad(xs, Cp, geom.kt, geom.kh, geom.kw, geom.pt, geom.ph, geom.pw, ctx.w_shapes[0], (B, T, H, W))
+                dw = g.view(cout, geom.kt, geom.kh, geom.kw, Cp)[..., :C].permute(0, 4, 1, 2, 3)
             if x2i is not None:
                 c1 = x2i.shape[1]
                 if need[3]:
@@ -451,17 +484,19 @@ class _Conv3dFn(torch.autograd.Function):
                     dw2 = g.view(cout, 1, 1, 1, c1).permute(0, 4, 1, 2, 3)
         elif geom.strided_implicit:
             if need[0]:
-                dx = empty_internal(B, C, T, H, W, bf16, dev)
+                dx = empty_internal(B, Cp, T, H, W, bf16, dev)
                 _conv_call('dgrad', 2.0 * B * To * Ho * Wo * cout * geom.k_main,
                            'og_conv3d_strided_dgrad', dyb.data_ptr(), cpad, cout, packed.data_ptr(), ldw, geom.kt, geom.kh,
-                           geom.kw, geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), B, T, H, W, C, s)
+                           geom.kw, geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, dx.data_ptr(), B, T, H, W, Cp, s)
+                if geom.padded:
+                    dx = dx[:, :C]
             if need[1]:
                 rows = cpad if cpad != cout else cout
-                g = _zeros((rows, geom.ntaps * C), f32, dev)
+                g = _zeros((rows, geom.ntaps * Cp), f32, dev)
                 _conv_call('wgrad', 2.0 * B * To * Ho * Wo * cout * geom.k_main,
-                           'og_conv3d_strided_wgrad', dyb.data_ptr(), cpad, xs.data_ptr(), C, g.data_ptr(), g.shape[1],
+                           'og_conv3d_strided_wgrad', dyb.data_ptr(), cpad, xs.data_ptr(), Cp, g.data_ptr(), g.shape[1],
                            geom.kt, geom.kh, geom.kw, geom.st, geom.sh, geom.sw, geom.pt, geom.ph, geom.pw, B, T, H, W, s)
-                dw = g[:cout].view(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
+                dw = g[:cout].view(cout, geom.kt, geom.kh, geom.kw, Cp)[..., :C].permute(0, 4, 1, 2, 3)
         else:
             col = xs
             if need[0]:
@@ -482,11 +517,11 @@ class _Conv3dFn(torch.autograd.Function):
                 db = dbs
             if ctx.has_bias[1] and need[5]:
                 db2 = dbs if db is None else dbs.clone()
-        return dx, dw, db, dx2, dw2, db2, None, None, None
+        return dx, dw, db, dx2, dw2, db2, None, None, None, (dyb[:, :cout] if ctx.has_residual else None)
 
 
-def conv3d(x, weight, bias, packed, geom, out_f32=False, x2=None, weight2=None, bias2=None):
-    return _Conv3dFn.apply(x, weight, bias, x2, weight2, bias2, packed, geom, out_f32)
+def conv3d(x, weight, bias, packed, geom, out_f32=False, x2=None, weight2=None, bias2=None, residual=None):
+    return _Conv3dFn.apply(x, weight, bias, x2, weight2, bias2, packed, geom, out_f32, residual)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -556,23 +591,37 @@ class _GroupNormActFn(torch.autograd.Function):
         return dx, dgamma, dbeta, dcs, dcsh, None, None, None
 
 
+ACT_CODES = {'none': 0, None: 0, 'silu': 1, 'swish': 1, 'leaky': 2, 'leaky_relu': 2, 'relu': 3}
+
+
+def act_code(act) -> int:
+    """Activation name -> kernel code (csrc/norm_act.cu): 0 identity, 1 SiLU, 2 LeakyReLU(0.01), 3 ReLU."""
+    if isinstance(act, int):
+        return act
+    if act not in ACT_CODES:
+        raise ValueError(f'unknown activation {act!r}')
+    return ACT_CODES[act]
+
+
 def group_norm_act(x, gamma, beta, num_groups, eps=1e-5, act='none', cond_scale=None, cond_shift=None):
-    return _GroupNormActFn.apply(x, gamma, beta, cond_scale, cond_shift, num_groups, eps, 1 if act == 'silu' else 0)
+    return _GroupNormActFn.apply(x, gamma, beta, cond_scale, cond_shift, num_groups, eps, act_code(act))
 
 
 class _ActFn(torch.autograd.Function):
-    """Stand-alone SiLU (blueprint entry 'silu', genie/tokenizer.py:79,167): y = silu(x)."""
+    """Stand-alone activation y = act(scale * x): blueprint entry 'silu' (genie/tokenizer.py:79,167), the discriminators'
+    nn.LeakyReLU() (discriminator.py:97), VGG's ReLU, and plain scaling (act = 0)."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, act: int, scale: float):
         xi = to_internal(x, bf16)
         B, C, T, H, W = xi.shape
         dev = xi.device
-        A = torch.ones((B, C), dtype=f32, device=dev)
+        A = torch.full((B, C), float(scale), dtype=f32, device=dev)
         Bc = torch.zeros((B, C), dtype=f32, device=dev)
         y = empty_internal(B, C, T, H, W, bf16, dev)
-        _lib.call('og_affine_act_fwd', xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), y.data_ptr(), B, T * H * W, C, 1,
+        _lib.call('og_affine_act_fwd', xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), y.data_ptr(), B, T * H * W, C, act,
                   _stream())
+        ctx.act = act
         ctx.save_for_backward(xi, A, Bc)
         return y
 
@@ -583,12 +632,17 @@ class _ActFn(torch.autograd.Function):
         dyb = _as_bf16_rows(dy, C, C)
         dx = empty_internal(B, C, T, H, W, bf16, xi.device)
         _lib.call('og_affine_act_bwd_apply', dyb.data_ptr(), xi.data_ptr(), A.data_ptr(), Bc.data_ptr(), None, None,
-                  None, dx.data_ptr(), 1, B, T * H * W, C, _stream())
-        return dx
+                  None, dx.data_ptr(), ctx.act, B, T * H * W, C, _stream())
+        return dx, None, None
 
 
 def silu(x):
-    return _ActFn.apply(x)
+    return _ActFn.apply(x, 1, 1.0)
+
+
+def activation(x, act='none', scale: float = 1.0):
+    """y = act(scale * x) on an internal-format (C % 8 == 0) tensor."""
+    return _ActFn.apply(x, act_code(act), float(scale))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -616,6 +670,34 @@ class _PixelShuffleFn(torch.autograd.Function):
 
 def pixel_shuffle3d(x, p, q, r):
     return _PixelShuffleFn.apply(x, p, q, r)
+
+
+class _SpaceToDepthFn(torch.autograd.Function):
+    """'b c (t p) (h q) (w r) -> b (c p q r) t h w' — the inverse shuffle, forward op of SpaceDownsample
+    (genie/module/image.py:92-95 with p = 1). Same kernel as _PixelShuffleFn run in its other direction."""
+
+    @staticmethod
+    def forward(ctx, x, p: int, q: int, r: int):
+        xi = to_internal(x, bf16)
+        B, c, Tp, Hq, Wr = xi.shape
+        assert Tp % p == 0 and Hq % q == 0 and Wr % r == 0, 'space_to_depth: extents must divide by the factors'
+        T, H, W = Tp // p, Hq // q, Wr // r
+        y = empty_internal(B, c * p * q * r, T, H, W, bf16, xi.device)
+        _lib.call('og_pixel_shuffle3d', y.data_ptr(), xi.data_ptr(), 1, B, T, H, W, c, p, q, r, _stream())
+        ctx.cfg = (B, c, T, H, W, p, q, r)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, c, T, H, W, p, q, r = ctx.cfg
+        dyb = _as_bf16_rows(dy, c * p * q * r, c * p * q * r)
+        dx = empty_internal(B, c, T * p, H * q, W * r, bf16, dy.device)
+        _lib.call('og_pixel_shuffle3d', dyb.data_ptr(), dx.data_ptr(), 0, B, T, H, W, c, p, q, r, _stream())
+        return dx, None, None, None
+
+
+def space_to_depth3d(x, p, q, r):
+    return _SpaceToDepthFn.apply(x, p, q, r)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -921,7 +1003,7 @@ def linear_rows(x2d: Tensor, weight: Tensor, bias: Optional[Tensor], packed: Ten
     N = weight.shape[0]
     geom = ConvGeom(K, N, (1, 1, 1))
     x5 = x2d.reshape(1, 1, 1, rows, K).permute(0, 4, 1, 2, 3)
-    y5 = _Conv3dFn.apply(x5, weight.view(N, K, 1, 1, 1), bias, None, None, None, packed, geom, out_f32)
+    y5 = _Conv3dFn.apply(x5, weight.view(N, K, 1, 1, 1), bias, None, None, None, packed, geom, out_f32, None)
     return y5.permute(0, 2, 3, 4, 1).reshape(rows, N)
 
 
@@ -1031,7 +1113,7 @@ class _ResBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_sums, g1w, g1b, w1, b1, g2w, g2b, w2, b2, wres, bres, packed1, packed2, geom1: ConvGeom,
-                geom2: ConvGeom, G: int, eps: float):
+                geom2: ConvGeom, G: int, eps: float, act: int = 1):
         _require_cuda(x, 'residual block input')
         xi = to_internal(x, bf16)
         B, C0, T, H, W = xi.shape
@@ -1046,7 +1128,7 @@ class _ResBlockFn(torch.autograd.Function):
         A1, B1 = torch.empty((B, C0), dtype=f32, device=dev), torch.empty((B, C0), dtype=f32, device=dev)
         A2, B2 = torch.empty((B, C1), dtype=f32, device=dev), torch.empty((B, C1), dtype=f32, device=dev)
         a1 = empty_internal(B, C0, T, H, W, bf16, dev)
-        _lib.call('og_gn_act_fwd', xi.data_ptr(), x_sums.data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, None, eps, G, 1,
+        _lib.call('og_gn_act_fwd', xi.data_ptr(), x_sums.data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, None, eps, G, act,
                   a1.data_ptr(), A1.data_ptr(), B1.data_ptr(), mr[0].data_ptr(), B, V, C0, s)
         ws = _workspace(dev, B * V * C1 * 4)
         fuse_stats = G == 1 and FUSE_STATS
@@ -1059,7 +1141,7 @@ class _ResBlockFn(torch.autograd.Function):
         if not fuse_stats:
             _lib.call('og_gn_stats', h1.data_ptr(), B, V, C1, G, sums2.data_ptr(), s)
         a2 = empty_internal(B, C1, T, H, W, bf16, dev)
-        _lib.call('og_gn_act_fwd', h1.data_ptr(), sums2.data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, None, eps, G, 1,
+        _lib.call('og_gn_act_fwd', h1.data_ptr(), sums2.data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, None, eps, G, act,
                   a2.data_ptr(), A2.data_ptr(), B2.data_ptr(), mr[1].data_ptr(), B, V, C1, s)
         y = empty_internal(B, C1, T, H, W, bf16, dev)
         y_sums = _zeros((B, 1, 2), torch.float64, dev)
@@ -1069,7 +1151,7 @@ class _ResBlockFn(torch.autograd.Function):
                    y_sums.data_ptr() if FUSE_STATS else None, s)
         if not FUSE_STATS:
             _lib.call('og_gn_stats', y.data_ptr(), B, V, C1, 1, y_sums.data_ptr(), s)
-        ctx.cfg = (geom1, geom2, G, b1 is not None, b2 is not None, bres is not None)
+        ctx.cfg = (geom1, geom2, G, b1 is not None, b2 is not None, bres is not None, act)
         ctx.save_for_backward(xi, a1, h1, a2, A1, B1, A2, B2, mr, g1w, g1b, g2w, g2b, packed1, packed2)
         ctx.mark_non_differentiable(y_sums)
         return y, y_sums
@@ -1077,7 +1159,7 @@ class _ResBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dsums):
         xi, a1, h1, a2, A1, B1, A2, B2, mr, g1w, g1b, g2w, g2b, packed1, packed2 = ctx.saved_tensors
-        geom1, geom2, G, has_b1, has_b2, has_bres = ctx.cfg
+        geom1, geom2, G, has_b1, has_b2, has_bres, act = ctx.cfg
         B, C0, T, H, W = xi.shape
         C1 = geom1.cout
         V = T * H * W
@@ -1103,16 +1185,16 @@ class _ResBlockFn(torch.autograd.Function):
         d_a2 = empty_internal(B, C1, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * geom2.k_main, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(),
                    ld2, 0, geom2.kt, geom2.kh, geom2.kw, geom2.pt, geom2.ph, geom2.pw, d_a2.data_ptr(), 0, B, T, H, W, C1,
-                   ws.data_ptr(), ws.numel(), *((h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1, S2.data_ptr())
+                   ws.data_ptr(), ws.numel(), *((h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), act, S2.data_ptr())
                                                 if FUSE_RED else (None, None, None, 0, None)), s)
         if not FUSE_RED:
-            _lib.call('og_affine_act_bwd_reduce', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), 1,
+            _lib.call('og_affine_act_bwd_reduce', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), act,
                       S2.data_ptr(), B, V, C1, s)
         small = _zeros((3, C1), f32, dev)              # dgamma2, dbeta2, db1 in one fill
         dg2w, dg2b, db1 = small[0], small[1], small[2]
         d_h1 = empty_internal(B, C1, T, H, W, bf16, dev)
         _lib.call('og_gn_act_bwd', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), S2.data_ptr(),
-                  mr[1].data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, G, 1, None, d_h1.data_ptr(), dg2w.data_ptr(),
+                  mr[1].data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, G, act, None, d_h1.data_ptr(), dg2w.data_ptr(),
                   dg2b.data_ptr(), None, None, db1.data_ptr() if has_b1 else None, B, V, C1, s)
         dw1 = wgrad(d_h1, C1, a1, C0, geom1)
         dx = None
@@ -1123,10 +1205,10 @@ class _ResBlockFn(torch.autograd.Function):
         _conv_call('dgrad', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_dgrad', d_h1.data_ptr(), C1, C1,
                    packed1.data_ptr(), packed1.shape[1], 0, geom1.kt, geom1.kh, geom1.kw, geom1.pt, geom1.ph, geom1.pw,
                    d_a1.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
-                   *((xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), 1, S1.data_ptr()) if FUSE_RED
+                   *((xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), act, S1.data_ptr()) if FUSE_RED
                      else (None, None, None, 0, None)), s)
         if not FUSE_RED:
-            _lib.call('og_affine_act_bwd_reduce', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), 1,
+            _lib.call('og_affine_act_bwd_reduce', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), act,
                       S1.data_ptr(), B, V, C0, s)
         dx_res = empty_internal(B, C0, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
@@ -1135,12 +1217,13 @@ class _ResBlockFn(torch.autograd.Function):
         # (the input gradient is always produced: its pass is also what emits dgamma1 / dbeta1)
         dx = empty_internal(B, C0, T, H, W, bf16, dev)
         _lib.call('og_gn_act_bwd', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), S1.data_ptr(),
-                  mr[0].data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, G, 1, dx_res.data_ptr(), dx.data_ptr(),
+                  mr[0].data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, G, act, dx_res.data_ptr(), dx.data_ptr(),
                   dg1w.data_ptr(), dg1b.data_ptr(), None, None, None, B, V, C0, s)
         return (dx, None, dg1w, dg1b, dw1, db1 if has_b1 else None, dg2w, dg2b, dw2, db2 if has_b2 else None, dwres,
-                (db2.clone() if has_b2 else db2) if has_bres else None, None, None, None, None, None, None)
+                (db2.clone() if has_b2 else db2) if has_bres else None, None, None, None, None, None, None, None)
 
 
-def residual_block(x, x_sums, g1w, g1b, w1, b1, g2w, g2b, w2, b2, wres, bres, packed1, packed2, geom1, geom2, G, eps):
+def residual_block(x, x_sums, g1w, g1b, w1, b1, g2w, g2b, w2, b2, wres, bres, packed1, packed2, geom1, geom2, G, eps,
+                   act='silu'):
     return _ResBlockFn.apply(x, x_sums, g1w, g1b, w1, b1, g2w, g2b, w2, b2, wres, bres, packed1, packed2, geom1, geom2, G,
-                             float(eps))
+                             float(eps), act_code(act))

@@ -145,10 +145,10 @@ class FusedAdamW(Optimizer):
                 t.n = p.numel()
                 tgt = self._bf16_target(p)
                 if tgt is not None:
-                    packed, col_off = tgt
+                    packed, col_off = tgt[0], tgt[1]
                     t.p_bf16 = packed.data_ptr() + 2 * col_off
-                    t.row_len = p.numel() // p.shape[0]
-                    t.dst_ld = packed.shape[1]
+                    t.row_len = tgt[2] if len(tgt) > 2 else p.numel() // p.shape[0]
+                    t.dst_ld = tgt[3] if len(tgt) > 2 else packed.shape[1]
                 else:
                     t.p_bf16, t.row_len, t.dst_ld = None, 1, 1
             raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).pin_memory()

@@ -1,9 +1,9 @@
 """VideoTokenizer — the reference's Lightning surface (genie/tokenizer.py:225-442) on the B200 hot path.
 
 Same constructor signature, blueprints, method names, return tuples, logged metric keys and state_dict
-keys. The GAN and perceptual terms (genie/module/loss.py, discriminator.py) are outside the hot-path
-scope: they must be disabled (weights 0), which is also the only configuration in which
-the reference itself runs offline (its VGG weights need a download)."""
+keys, including the GAN (frame critic, hinge losses) and perceptual (VGG16 feature distance) terms of
+genie/module/loss.py — see open_genie_b200/module/loss.py for the two facts that matter there (the perceptual
+term carries no gradient in the reference; VGG16 weights cannot be downloaded offline)."""
 from __future__ import annotations
 
 from typing import Any, Callable, Dict, Iterable, Tuple
@@ -122,10 +122,6 @@ class VideoTokenizer(LightningModule):
         quant_loss_weight: float = 1.,
     ) -> None:
         super().__init__()
-        if gan_loss_weight > 0 or perc_loss_weight > 0:
-            raise NotImplementedError(
-                'The GAN and perceptual losses (genie/module/loss.py, discriminator.py) are outside the B200 '
-                'hot-path scope; construct VideoTokenizer(..., gan_loss_weight=0, perc_loss_weight=0).')
         self.optimizer = optimizer
         self.enc_layers, self.enc_ext = parse_blueprint(enc_desc)
         self.dec_layers, self.dec_ext = parse_blueprint(dec_desc)
@@ -136,8 +132,13 @@ class VideoTokenizer(LightningModule):
             codebook_dim=d_codebook, num_codebook=n_codebook, input_dim=last_enc_dim, use_bias=lfq_bias,
             frac_sample=lfq_frac_sample, commit_weight=lfq_commit_weight, entropy_weight=lfq_entropy_weight,
             diversity_weight=lfq_diversity_weight)
-        self.perc_crit = nn.Identity()
-        self.gan_crit = nn.Identity()
+        # auxiliary objectives (genie/tokenizer.py:288-299); a disabled term is identically zero here (the reference
+        # calls nn.Identity()(rec, video, train_gen=True) in that case and raises)
+        from .module.loss import GANLoss, PerceptualLoss
+        self.perc_crit = PerceptualLoss(model_name=perceptual_model, feat_layers=perc_feat_layers,
+                                        num_frames=gan_frames_per_batch) if perc_loss_weight > 0 else nn.Identity()
+        self.gan_crit = GANLoss(discriminate=gan_discriminate, num_frames=gan_frames_per_batch,
+                                **disc_kwargs) if gan_loss_weight > 0 else nn.Identity()
         self.gan_loss_weight = gan_loss_weight
         self.perc_loss_weight = perc_loss_weight
         self.quant_loss_weight = quant_loss_weight
@@ -182,14 +183,20 @@ class VideoTokenizer(LightningModule):
         (quant_video, idxs), quant_loss = self.quant(enc_video, beta=beta, transpose=transpose)
         rec_video = self._decode_internal(quant_video)
         rec_loss = ops.mse_loss(rec_video, video)
-        zero = rec_loss.new_zeros(())
+        gen_loss = dis_loss = perc_loss = 0.
+        if self.gan_loss_weight > 0:           # hinge GAN on randomly picked frames (tokenizer.py:367-368)
+            gen_loss = self.gan_crit(rec_video, video, train_gen=True)
+            dis_loss = self.gan_crit(rec_video, video, train_gen=False)
+        if self.perc_loss_weight > 0:          # VGG16 feature distance (tokenizer.py:371); carries no gradient
+            perc_loss = self.perc_crit(rec_video, video)
         # the reference's operator precedence (lines 375-379): in eval mode (quant_loss None) the loss is 0
-        loss = (rec_loss + quant_loss * self.quant_loss_weight) if exists(quant_loss) else 0
+        loss = (rec_loss + gen_loss * self.gan_loss_weight + dis_loss * self.gan_loss_weight
+                + perc_loss * self.perc_loss_weight + quant_loss * self.quant_loss_weight) if exists(quant_loss) else 0
         return loss, (
             rec_loss,
-            zero if self.gan_loss_weight > 0 else 0,
-            zero if self.gan_loss_weight > 0 else 0,
-            zero if self.perc_loss_weight > 0 else 0,
+            gen_loss if self.gan_loss_weight > 0 else 0,
+            dis_loss if self.gan_loss_weight > 0 else 0,
+            perc_loss if self.perc_loss_weight > 0 else 0,
             quant_loss if exists(quant_loss) and self.quant_loss_weight > 0 else 0,
         )
 

@@ -263,6 +263,62 @@ def gen_blur2d():
     torch.save(out, os.path.join(OUT, 'blur2d.pt'))
 
 
+def gen_gan_perceptual():
+    """GAN critic + hinge losses + perceptual loss (genie/module/discriminator.py, loss.py) run by the real reference.
+    Test seams: torch.randperm is replaced by fixed permutations (frame picking), VGG16 gets closed-form weights
+    (`weights='DEFAULT'` needs a download)."""
+    from genie.module.discriminator import FrameDiscriminator
+    from genie.module.loss import GANLoss, PerceptualLoss
+    out = {}
+    disc = FrameDiscriminator(inp_size=32)
+    sd = load_det(disc)
+    frames = O.det_uniform('gan.frames', (4, 3, 32, 32))
+    frames.requires_grad_(True)
+    score = disc(frames)
+    (-score.mean()).backward()
+    out['disc'] = {'score': score.detach(), 'dframes': frames.grad.clone(), 'grads': summarize_grads(grads_of(disc))}
+    # hinge losses through GANLoss with fixed frame picks
+    b, t, k = 2, 8, 2
+    perms = [torch.tensor([3, 0, 5, 1, 7, 2, 6, 4]), torch.tensor([6, 2, 1, 7, 0, 4, 3, 5])]
+    idxs = torch.cat([p[:k] for p in perms])
+    real_randperm = torch.randperm
+
+    def fixed_perms():
+        it = iter(perms * 8)
+        return lambda n, **kw: next(it)
+
+    gan = GANLoss(discriminate='frames', num_frames=k, inp_size=32)
+    gan.disc.load_state_dict(sd)
+    rec = O.det_uniform('gan.rec', (b, 3, t, 32, 32))
+    rec.requires_grad_(True)
+    inp = O.det_uniform('gan.inp', (b, 3, t, 32, 32))
+    torch.randperm = fixed_perms()
+    try:
+        gen_loss = gan(rec, inp, train_gen=True)
+        torch.randperm = fixed_perms()
+        dis_loss = gan(rec, inp, train_gen=False)
+    finally:
+        torch.randperm = real_randperm
+    (gen_loss + dis_loss).backward()
+    out['gan'] = {'frames_idxs': idxs, 'gen_loss': gen_loss.detach(), 'dis_loss': dis_loss.detach(),
+                  'drec': rec.grad.clone(), 'grads': summarize_grads(grads_of(gan))}
+    # perceptual loss, closed-form VGG16 feature weights
+    perc = PerceptualLoss(model_weights=None, num_frames=k)
+    vsd = O.det_state_dict({k_: tuple(v.shape) for k_, v in perc.percept_model.state_dict().items()
+                            if k_.startswith('features')}, gain=1.4)
+    perc.percept_model.load_state_dict(vsd, strict=False)
+    torch.randperm = fixed_perms()
+    try:
+        with torch.no_grad():
+            pl = perc(rec.detach(), inp)
+    finally:
+        torch.randperm = real_randperm
+    assert not pl.requires_grad
+    out['perc'] = {'frames_idxs': idxs, 'loss': pl.detach()}
+    print(f'  gan: gen {gen_loss.item():.5f} dis {dis_loss.item():.5f}; perceptual {pl.item():.6f}')
+    torch.save(out, os.path.join(OUT, 'gan_perceptual.pt'))
+
+
 def gen_generate():
     """DynamicsModel.generate run by the REAL reference with two test seams: torch.multinomial is replaced by the
     inverse-CDF draw on injected uniforms (O.inverse_cdf_draw) and, for the big case, forward() returns given logits."""
@@ -321,10 +377,14 @@ if __name__ == '__main__':
         with torch.no_grad():
             gen_generate()
         sys.exit(0)
+    if sys.argv[1:] == ['gan']:
+        gen_gan_perceptual()
+        sys.exit(0)
     with torch.no_grad():
         gen_kats()
         gen_generate()
     gen_blur2d()
+    gen_gan_perceptual()
     gen_layers()
     gen_lfq()
     gen_st_block()

@@ -95,6 +95,47 @@ def test_strided_causal_conv_implicit_gemm(cin, cout, stride, shape):
     assert_close(grads['go_down.conv3d.weight'], w.grad, 2e-3, 1e-3 * w.grad.abs().max().item(), 'strided implicit wgrad')
 
 
+@pytest.mark.parametrize('cin,cout,stride,shape', [
+    (3, 128, (1, 1, 1), (2, 3, 4, 16, 16)),          # tokenizer / LatentAction stem: 3 -> C
+    (18, 64, (1, 1, 1), (2, 18, 2, 8, 8)),           # decoder stem: 18 -> C (its input needs a gradient: LFQ backward)
+    (3, 64, (1, 4, 4), (1, 3, 2, 16, 16)),           # REPR_TOK_ENC: strided AND narrow
+])
+def test_narrow_cin_conv_is_an_implicit_gemm_on_padded_channels(cin, cout, stride, shape):
+    from open_genie_b200.module.video import CausalConv3d
+    from open_genie_b200 import _lib
+    m = CausalConv3d(cin, cout, 3, stride=stride)
+    g = m.conv3d.geom
+    assert g.padded and g.cin_pad == 64 and (g.direct or g.strided_implicit)
+    sd = det_weights(m)
+    m.to(DEV)
+    m.out_f32 = True
+    x = bf16_round(O.det_uniform('narrow.x', shape))
+    _lib.TIMING = []
+    try:
+        y, dx, grads = _run_layer(m, x)
+        names = {t[0] for t in _lib.TIMING}
+    finally:
+        _lib.TIMING = None
+    assert not any('im2col' in n or 'col2im' in n for n in names), names
+    sdr = round_conv_weights(sd)
+    xr = x.clone().requires_grad_(True)
+    w = sdr['conv3d.weight'].clone().requires_grad_(True)
+    yo = O.causal_conv3d(xr, w, sdr['conv3d.bias'], stride=stride)
+    assert_close(y, yo, 1e-3, 1e-5 * yo.abs().max().item(), 'narrow fwd')
+    yo.backward(bf16_round((2.0 / yo.numel()) * y))
+    assert dx.shape == xr.grad.shape
+    assert_close(dx, xr.grad, BF16_ULP, BF16_ULP * xr.grad.abs().max().item(), 'narrow dgrad')
+    assert grads['conv3d.weight'].shape == w.grad.shape
+    assert_close(grads['conv3d.weight'], w.grad, 2e-3, 1e-3 * w.grad.abs().max().item(), 'narrow wgrad')
+    # the optimizer refreshes the channel-padded bf16 operand in place
+    from open_genie_b200.optim import FusedAdamW
+    opt = FusedAdamW(m.parameters(), lr=0.05)
+    opt.step()
+    packed = m.conv3d.packed().float().view(cout, 27, 64)
+    wnow = m.conv3d.weight.detach().permute(0, 2, 3, 4, 1).reshape(cout, 27, cin)
+    assert torch.equal(packed[:, :, :cin], wnow.to(torch.bfloat16).float()) and float(packed[:, :, cin:].abs().max()) == 0.0
+
+
 def test_spacetime_downsample_im2col_path(golden, monkeypatch):
     monkeypatch.setenv('OG_STRIDED_IM2COL', '1')        # the explicit path stays available for Cin not in 64Z
     from open_genie_b200.module.video import SpaceTimeDownsample

@@ -56,9 +56,23 @@ def test_state_dict_matches_the_reference(golden):
     assert torch.equal(tok.state_dict()[k], sd[k])
 
 
-def test_tokenizer_rejects_out_of_scope_losses():
-    with pytest.raises(NotImplementedError, match='GAN and perceptual'):
-        og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6)
+def test_tokenizer_builds_the_auxiliary_losses_like_the_reference():
+    """genie/tokenizer.py:288-299: GANLoss(FrameDiscriminator(**disc_kwargs)) and PerceptualLoss(vgg16) when their
+    weights are > 0 (the constructor defaults), nn.Identity otherwise; the 'video' critic is out of scope."""
+    import torch.nn as nn
+    from open_genie_b200.module.loss import GANLoss, PerceptualLoss
+    tok = og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6, disc_kwargs={'inp_size': 32})
+    assert isinstance(tok.gan_crit, GANLoss) and isinstance(tok.perc_crit, PerceptualLoss)
+    keys = set(tok.state_dict())
+    assert {'gan_crit.disc.proj_in.weight', 'gan_crit.disc.core.1.0.main.6.go_up.1.weight',
+            'gan_crit.disc.to_logits.3.weight', 'perc_crit.percept_model.features.0.weight',
+            'perc_crit.percept_model.features.28.bias'} <= keys
+    assert tok.state_dict()['gan_crit.disc.proj_in.weight'].shape == (64, 3, 3, 3)        # nn.Conv2d layout
+    assert not any(p.requires_grad for p in tok.perc_crit.parameters())                   # frozen extractor (loss.py:49-51)
+    tok0 = og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6, gan_loss_weight=0, perc_loss_weight=0)
+    assert isinstance(tok0.gan_crit, nn.Identity) and isinstance(tok0.perc_crit, nn.Identity)
+    with pytest.raises(NotImplementedError, match='VideoDiscriminator'):
+        og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6, gan_discriminate='video', disc_kwargs={'inp_size': (8, 32)})
 
 
 def test_conv_geometry():
@@ -67,9 +81,11 @@ def test_conv_geometry():
     g = ops.ConvGeom(128, 128, (3, 3, 3), causal=False)
     assert (g.pt, g.direct) == (1, True)
     g = ops.ConvGeom(128, 128, (3, 3, 3), stride=(2, 2, 2))
-    assert (g.pt, g.direct, g.out_dims(16, 32, 32)) == (1, False, (8, 16, 16))
-    g = ops.ConvGeom(3, 128, (3, 3, 3))
-    assert not g.direct and g.kpad == 128 and g.k_main == 81
+    assert (g.pt, g.direct, g.strided_implicit, g.out_dims(16, 32, 32)) == (1, False, True, (8, 16, 16))
+    g = ops.ConvGeom(3, 128, (3, 3, 3))            # narrow Cin: implicit GEMM on a channel-padded input
+    assert g.direct and g.padded and g.cin_pad == 64 and g.kpad == 27 * 64 and g.k_main == 81
+    g = ops.ConvGeom(18, 512, (3, 3, 3))
+    assert g.direct and g.cin_pad == 64 and g.k_main == 18 * 27
     g = ops.ConvGeom(128, 128, (3, 3, 3), stride=(1, 2, 2))
     assert g.out_dims(16, 64, 64) == (16, 32, 32)
 
