@@ -269,12 +269,16 @@ int og_lfq_bwd(const float* x, int ldx, int64_t ntok, int D, float beta, float w
 /* y = LayerNorm(RoPE(x)): RotaryEmbedding.forward/apply (attention.py:48-94: interleaved pairs over the full
  * channel dim, fp32 angle = pos * freq[i]) followed by nn.LayerNorm (attention.py:219-220).
  * pos(row) = (row / pos_div) % pos_mod — spatial: (1, H*W); temporal: (H*W, T). freq: fp32 [C/2]. */
+/* cos_sin (optional, both passes): fp32 [pos_mod][C/2][2] = (cos, sin)(pos * freq[i]) written by og_rope_table — the
+ * same sincosf values the passes would otherwise evaluate per element (the '2d' angles reach ~4000 rad: sincosf's slow
+ * range reduction made these passes SM-bound at 0.4 of the HBM roofline). Results are bit-identical with and without. */
+int og_rope_table(const float* freq, int npos, int C, float* table, og_stream_t stream);
 int og_rope_ln_fwd(const void* x, const float* freq, const float* gamma, const float* beta, float eps, void* y,
-                   int64_t rows, int C, int64_t pos_div, int pos_mod, og_stream_t stream);
+                   int64_t rows, int C, int64_t pos_div, int pos_mod, const float* cos_sin, og_stream_t stream);
 /* dx = RoPE^T(LN'(g0 + g1 + g2)) + add ; dgamma/dbeta accumulated (+=). g1, g2, add may be NULL. */
 int og_rope_ln_bwd(const void* x, const float* freq, const float* gamma, float eps, const void* g0, const void* g1,
                    const void* g2, const void* add, void* dx, float* dgamma, float* dbeta, int64_t rows, int C,
-                   int64_t pos_div, int pos_mod, og_stream_t stream);
+                   int64_t pos_div, int pos_mod, const float* cos_sin, og_stream_t stream);
 
 /* Spatial attention: F.scaled_dot_product_attention(q,k,v, scale) non-causal (attention.py:229-234) on
  * tcgen05 tensor cores. q,k,v,out: [nseq][S][C], C = n_head*64. lse: fp32 [nseq][n_head][S] (saved for backward).

@@ -85,7 +85,8 @@ template <int NCH>
 __global__ void __launch_bounds__(256)
     og_rope_ln_fwd_vec_kernel(const uint4* __restrict__ x, const float* __restrict__ freq,
                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                              uint4* __restrict__ y, long long rows, long long pos_div, int pos_mod) {
+                              uint4* __restrict__ y, long long rows, long long pos_div, int pos_mod,
+                              const float4* __restrict__ tab) {
   constexpr int NP = 4 * NCH;
   constexpr int C = 256 * NCH;
   constexpr int VPR = 32 * NCH;
@@ -105,11 +106,25 @@ __global__ void __launch_bounds__(256)
       bt1[4 * j + e] = __ldg(beta + 2 * p + 1);
     }
   for (long long row = warp0; row < rows; row += nwarps) {
-    const float pos = (float)((row / pos_div) % pos_mod);
+    const int ipos = (int)((row / pos_div) % pos_mod);
+    const float pos = (float)ipos;
     const long long vb = row * VPR + lane;
     uint4 ux[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) ux[j] = __ldg(x + vb + 32 * j);
+    // (cos, sin) of this row's position: from the precomputed table (og_rope_table: the same sincosf values, computed
+    // once per (frequencies, sequence length) instead of once per element — the '2d' angles reach ~4000 rad, where
+    // sincosf takes its slow range-reduction path and made this pass SM-bound at 0.4 of the HBM roofline)
+    float tcs[NP], tsn[NP];
+    if (tab) {
+      const float4* tr = tab + (long long)ipos * (C / 4);      // row of C/2 (cos, sin) pairs = C/4 float4
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const float4 t0 = __ldg(tr + 64 * j + 2 * lane), t1 = __ldg(tr + 64 * j + 2 * lane + 1);
+        tcs[4 * j] = t0.x; tsn[4 * j] = t0.y; tcs[4 * j + 1] = t0.z; tsn[4 * j + 1] = t0.w;
+        tcs[4 * j + 2] = t1.x; tsn[4 * j + 2] = t1.y; tcs[4 * j + 3] = t1.z; tsn[4 * j + 3] = t1.w;
+      }
+    }
     float r0[NP], r1[NP];
     float s = 0.f;
 #pragma unroll
@@ -120,7 +135,12 @@ __global__ void __launch_bounds__(256)
         const int i = 4 * j + e;
         const float2 v = __bfloat1622float2(h[e]);
         float sn, cs;
-        sincosf(pos * fq[i], &sn, &cs);
+        if (tab) {
+          sn = tsn[i];
+          cs = tcs[i];
+        } else {
+          sincosf(pos * fq[i], &sn, &cs);
+        }
         r0[i] = v.x * cs - v.y * sn;
         r1[i] = v.y * cs + v.x * sn;
         s += r0[i] + r1[i];
@@ -275,7 +295,8 @@ __global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
                               const float* __restrict__ gamma, float eps, const uint4* __restrict__ g0,
                               const uint4* __restrict__ g1, const uint4* __restrict__ g2,
                               const uint4* __restrict__ add, uint4* __restrict__ dx, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta, long long rows, long long pos_div, int pos_mod) {
+                              float* __restrict__ dbeta, long long rows, long long pos_div, int pos_mod,
+                              const float4* __restrict__ tab) {
   constexpr int NP = 4 * NCH;      // pairs per lane
   constexpr int C = 256 * NCH;
   constexpr int VPR = 32 * NCH;    // uint4 vectors per row
@@ -308,7 +329,8 @@ __global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
     }
   };
   for (long long row = warp0; row < rows; row += nwarps) {
-    const float pos = (float)((row / pos_div) % pos_mod);
+    const int ipos = (int)((row / pos_div) % pos_mod);
+    const float pos = (float)ipos;
     const long long vb = row * VPR + lane;
     uint4 ux[NCH], ug[NCH];
 #pragma unroll
@@ -317,6 +339,15 @@ __global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
       ug[j] = __ldg(g0 + vb + 32 * j);
     }
     float r0[NP], r1[NP], sn[NP], cs[NP];
+    if (tab) {   // see og_rope_ln_fwd_vec_kernel
+      const float4* tr = tab + (long long)ipos * (C / 4);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const float4 t0 = __ldg(tr + 64 * j + 2 * lane), t1 = __ldg(tr + 64 * j + 2 * lane + 1);
+        cs[4 * j] = t0.x; sn[4 * j] = t0.y; cs[4 * j + 1] = t0.z; sn[4 * j + 1] = t0.w;
+        cs[4 * j + 2] = t1.x; sn[4 * j + 2] = t1.y; cs[4 * j + 3] = t1.z; sn[4 * j + 3] = t1.w;
+      }
+    }
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
@@ -325,7 +356,7 @@ __global__ void __launch_bounds__(256, (NCH <= 2 ? 2 : 1))
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = 4 * j + e;
-        sincosf(pos * fq[i], &sn[i], &cs[i]);
+        if (!tab) sincosf(pos * fq[i], &sn[i], &cs[i]);
         r0[i] = a[e] * cs[i] - b[e] * sn[i];
         r1[i] = b[e] * cs[i] + a[e] * sn[i];
         s += r0[i] + r1[i];
@@ -688,7 +719,9 @@ __global__ void __launch_bounds__(128)
   if (kv_bcast) flush();
 }
 
-// experimental mma.sync path (temporal_attn_mma.cu): only with OG_TEMPORAL_MMA=1, d_head = 64, T <= 16
+// mma.sync m16n8k16 path (temporal_attn_mma.cu) for d_head = 64, T <= 16 — the default since round 2 (it passed the
+// parity suite on a B200 and took the LatentAction step from 246.9 to 220.1 ms, the Dynamics step from 20.5 to 16.5 ms:
+// profiles/r02f_configs*.jsonl); OG_TEMPORAL_MMA=0 selects the per-lane kernels below, which also cover T in (16, 32].
 int launch_temporal_fwd_mma(const void* q, const void* k, const void* v, const void* residual, void* out, int B, int T,
                             long long P, int C, int n_head, float scale, int kv_bcast, cudaStream_t stream);
 int launch_temporal_bwd_mma(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
@@ -696,7 +729,7 @@ int launch_temporal_bwd_mma(const void* q, const void* k, const void* v, const v
                             int kv_bcast, cudaStream_t stream);
 static bool temporal_mma_enabled(int D, int T, int C) {
   const char* e = getenv("OG_TEMPORAL_MMA");
-  return e && atoi(e) == 1 && D == 64 && T <= 16 && C % 8 == 0;
+  return !(e && atoi(e) == 0) && D == 64 && T <= 16 && C % 8 == 0;
 }
 
 static int row_grid(long long rows, int warps_per_block) {
@@ -712,7 +745,9 @@ static int row_grid(long long rows, int warps_per_block) {
 using namespace og;
 
 extern "C" int og_rope_ln_fwd(const void* x, const float* freq, const float* gamma, const float* beta, float eps,
-                              void* y, int64_t rows, int C, int64_t pos_div, int pos_mod, og_stream_t stream) {
+                              void* y, int64_t rows, int C, int64_t pos_div, int pos_mod, const float* cos_sin,
+                              og_stream_t stream) {
+  OG_REQUIRE(!cos_sin || (reinterpret_cast<uintptr_t>(cos_sin) & 15) == 0, "rope_ln_fwd: cos_sin must be 16-byte aligned");
   OG_REQUIRE(x && freq && gamma && beta && y && rows > 0, "rope_ln_fwd: bad arguments");
   OG_REQUIRE(C % 2 == 0 && C <= 2 * 32 * kMaxPairsPerLane, "rope_ln_fwd: C=%d must be even and <= 1024", C);
   if ((C == 256 || C == 512 || C == 1024) &&
@@ -720,11 +755,11 @@ extern "C" int og_rope_ln_fwd(const void* x, const float* freq, const float* gam
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = row_grid(rows, 8);
     if (C == 256)
-      og_rope_ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod);
+      og_rope_ln_fwd_vec_kernel<1><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod, (const float4*)cos_sin);
     else if (C == 512)
-      og_rope_ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod);
+      og_rope_ln_fwd_vec_kernel<2><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod, (const float4*)cos_sin);
     else
-      og_rope_ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod);
+      og_rope_ln_fwd_vec_kernel<4><<<grid, 256, 0, st>>>((const uint4*)x, freq, gamma, beta, eps, (uint4*)y, rows, pos_div, pos_mod, (const float4*)cos_sin);
     OG_CHECK_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
     return OG_OK;
@@ -736,9 +771,30 @@ extern "C" int og_rope_ln_fwd(const void* x, const float* freq, const float* gam
   return OG_OK;
 }
 
+// tab[pos][p] = (cos, sin)(pos * freq[p]) — exactly the values the passes would compute per element
+__global__ void og_rope_table_kernel(const float* __restrict__ freq, int npos, int pairs, float2* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npos * pairs) return;
+  const int pos = i / pairs, p = i - pos * pairs;
+  float sn, cs;
+  sincosf((float)pos * __ldg(freq + p), &sn, &cs);
+  tab[i] = make_float2(cs, sn);
+}
+
+extern "C" int og_rope_table(const float* freq, int npos, int C, float* table, og_stream_t stream) {
+  OG_REQUIRE(freq && table && npos > 0 && C > 0 && C % 2 == 0, "rope_table: bad arguments");
+  const int total = npos * (C / 2);
+  og_rope_table_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(freq, npos, C / 2, (float2*)table);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
 extern "C" int og_rope_ln_bwd(const void* x, const float* freq, const float* gamma, float eps, const void* g0,
                               const void* g1, const void* g2, const void* add, void* dx, float* dgamma, float* dbeta,
-                              int64_t rows, int C, int64_t pos_div, int pos_mod, og_stream_t stream) {
+                              int64_t rows, int C, int64_t pos_div, int pos_mod, const float* cos_sin,
+                              og_stream_t stream) {
+  OG_REQUIRE(!cos_sin || (reinterpret_cast<uintptr_t>(cos_sin) & 15) == 0, "rope_ln_bwd: cos_sin must be 16-byte aligned");
   OG_REQUIRE(x && freq && gamma && g0 && dx && dgamma && dbeta && rows > 0, "rope_ln_bwd: bad arguments");
   OG_REQUIRE(C % 2 == 0 && C <= 2 * 32 * kMaxPairsPerLane, "rope_ln_bwd: C=%d must be even and <= 1024", C);
   int grid = row_grid(rows, 8);
@@ -752,7 +808,8 @@ extern "C" int og_rope_ln_bwd(const void* x, const float* freq, const float* gam
 #define OG_ROPE_BWD(NCH)                                                                                          \
     og_rope_ln_bwd_vec_kernel<NCH><<<grid, 256, shb, st>>>((const uint4*)x, freq, gamma, eps, (const uint4*)g0,     \
                                                            (const uint4*)g1, (const uint4*)g2, (const uint4*)add,  \
-                                                           (uint4*)dx, dgamma, dbeta, rows, pos_div, pos_mod)
+                                                           (uint4*)dx, dgamma, dbeta, rows, pos_div, pos_mod,       \
+                                                           (const float4*)cos_sin)
     if (C == 256) OG_ROPE_BWD(1);
     else if (C == 512) OG_ROPE_BWD(2);
     else OG_ROPE_BWD(4);

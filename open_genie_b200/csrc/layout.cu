@@ -872,9 +872,10 @@ __global__ void og_frames_u8_to_video_kernel(const unsigned char* __restrict__ f
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const unsigned char* px = frames + i * 3;
-    const float c0 = (float)px[bgr ? 2 : 0] * (1.f / 255.f);
-    const float c1 = (float)px[1] * (1.f / 255.f);
-    const float c2 = (float)px[bgr ? 0 : 2] * (1.f / 255.f);
+    // IEEE division, not a multiply by the reciprocal: bit-identical to the reference's `torch.stack(frames) / 255.`
+    const float c0 = __fdiv_rn((float)px[bgr ? 2 : 0], 255.f);
+    const float c1 = __fdiv_rn((float)px[1], 255.f);
+    const float c2 = __fdiv_rn((float)px[bgr ? 0 : 2], 255.f);
     if (out_kind == 0) {
       const long long n = i / V, v = i - n * V;
       float* o = reinterpret_cast<float*>(out) + n * 3 * V + v;

@@ -225,10 +225,12 @@ __global__ void __launch_bounds__(256) og_affine_act_fwd_kernel(const uint4* __r
 // backward reduce: S[n][c] = (sum_v dpre, sum_v dpre * x), dpre = dy * act'(x*A+B)
 // grid (chunks, N), block 256; same thread mapping as the stats kernel.
 // ------------------------------------------------------------------------------------------------
+template <int ACT>
 __global__ void __launch_bounds__(256, 3)
     og_affine_act_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                     const float* __restrict__ A, const float* __restrict__ B, long long V, int C,
-                                    int act, long long rows_per_block, float* __restrict__ S) {
+                                    int /*act: template parameter ACT*/, long long rows_per_block, float* __restrict__ S) {
+  constexpr int act = ACT;  // compile-time: the per-element switch cost 20 % of the backward pass as a runtime value
   const int cvs = C >> 3;  // host guarantees cvs <= 256
   const int n = blockIdx.y;
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
@@ -374,12 +376,14 @@ __global__ void __launch_bounds__(256)
 // so the stand-alone finalize launch and the per-element coefficient loads disappear; block 0 of each
 // sample stores A, B and (mean, rstd) for the backward pass.
 // ------------------------------------------------------------------------------------------------
+template <int ACT>
 __global__ void __launch_bounds__(256, 4)
     og_gn_act_fwd_kernel(const uint4* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
                          const float* __restrict__ beta, const float* __restrict__ cond_scale,
                          const float* __restrict__ cond_shift, float* __restrict__ A, float* __restrict__ B,
                          float* __restrict__ mean_rstd, uint4* __restrict__ y, long long V, int C, int G,
-                         double inv_count, float eps, int act, long long rows_per_block) {
+                         double inv_count, float eps, int /*act: template parameter ACT*/, long long rows_per_block) {
+  constexpr int act = ACT;  // compile-time: the per-element switch cost 20 % of the backward pass as a runtime value
   const int cvs = C >> 3;
   const int n = blockIdx.y;
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
@@ -466,6 +470,7 @@ __global__ void __launch_bounds__(256, 4)
 // dgamma / dbeta / dcond. Optionally accumulates the per-channel column sum of dx (the bias gradient of
 // the convolution that produced x).
 // ------------------------------------------------------------------------------------------------
+template <int ACT>
 __global__ void __launch_bounds__(256, 3)
     og_gn_act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const float* __restrict__ A,
                          const float* __restrict__ B, const float* __restrict__ S, const float* __restrict__ mean_rstd,
@@ -473,7 +478,8 @@ __global__ void __launch_bounds__(256, 3)
                          const float* __restrict__ cond_scale, const uint4* __restrict__ add, uint4* __restrict__ dx,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcond_scale,
                          float* __restrict__ dcond_shift, float* __restrict__ dx_colsum, long long V, int C, int G,
-                         double inv_M, int act, long long rows_per_block) {
+                         double inv_M, int /*act: template parameter ACT*/, long long rows_per_block) {
+  constexpr int act = ACT;  // compile-time: the per-element switch cost 20 % of the backward pass as a runtime value
   const int cvs = C >> 3;
   const int n = blockIdx.y;
   const long long r_begin = (long long)blockIdx.x * rows_per_block;
@@ -669,8 +675,12 @@ extern "C" int og_affine_act_bwd_reduce(const void* dy, const void* x, const flo
   OG_REQUIRE(C % 8 == 0 && C <= 2048, "affine_act_bwd_reduce: C=%d must be a multiple of 8 and <= 2048", C);
   long long rpb;
   const dim3 grid = reduce_grid(N, V, &rpb, 6);
-  og_affine_act_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, V, C, act, rpb, S);
+#define OG_LAUNCH(ACT)                                                                                  \
+  og_affine_act_bwd_reduce_kernel<ACT><<<grid, 256, 0, (cudaStream_t)stream>>>(                          \
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, V, C, act, rpb, S)
+  OG_REQUIRE(act >= 0 && act <= 3, "affine_act_bwd_reduce: unknown activation code %d", act);
+  if (act == 0) OG_LAUNCH(0); else if (act == 1) OG_LAUNCH(1); else if (act == 2) OG_LAUNCH(2); else OG_LAUNCH(3);
+#undef OG_LAUNCH
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;
@@ -714,9 +724,13 @@ extern "C" int og_gn_act_fwd(const void* x, const double* sums, const float* gam
   long long rpb;
   const dim3 grid = reduce_grid(N, V, &rpb, 8);
   const double inv_count = 1.0 / ((double)V * (C / G));
-  og_gn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(x), sums, gamma, beta, cond_scale, cond_shift, A, B, mean_rstd,
-      reinterpret_cast<uint4*>(y), V, C, G, inv_count, eps, act, rpb);
+#define OG_LAUNCH(ACT)                                                                                  \
+  og_gn_act_fwd_kernel<ACT><<<grid, 256, 0, (cudaStream_t)stream>>>(                                     \
+      reinterpret_cast<const uint4*>(x), sums, gamma, beta, cond_scale, cond_shift, A, B, mean_rstd,     \
+      reinterpret_cast<uint4*>(y), V, C, G, inv_count, eps, act, rpb)
+  OG_REQUIRE(act >= 0 && act <= 3, "gn_act_fwd: unknown activation code %d", act);
+  if (act == 0) OG_LAUNCH(0); else if (act == 1) OG_LAUNCH(1); else if (act == 2) OG_LAUNCH(2); else OG_LAUNCH(3);
+#undef OG_LAUNCH
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;
@@ -734,10 +748,14 @@ extern "C" int og_gn_act_bwd(const void* dy, const void* x, const float* A, cons
   long long rpb;
   const dim3 grid = reduce_grid(N, V, &rpb, 6);
   const double inv_M = 1.0 / ((double)V * (C / G));
-  og_gn_act_bwd_kernel<<<grid, 256, dx_colsum ? 256 * 8 * sizeof(float) : 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, S, mean_rstd, gamma, beta, cond_scale,
-      reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), dgamma, dbeta, dcond_scale, dcond_shift,
-      dx_colsum, V, C, G, inv_M, act, rpb);
+#define OG_LAUNCH(ACT)                                                                                                    \
+  og_gn_act_bwd_kernel<ACT><<<grid, 256, dx_colsum ? 256 * 8 * sizeof(float) : 0, (cudaStream_t)stream>>>(                \
+      reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(x), A, B, S, mean_rstd, gamma, beta, cond_scale, \
+      reinterpret_cast<const uint4*>(add), reinterpret_cast<uint4*>(dx), dgamma, dbeta, dcond_scale, dcond_shift,         \
+      dx_colsum, V, C, G, inv_M, act, rpb)
+  OG_REQUIRE(act >= 0 && act <= 3, "gn_act_bwd: unknown activation code %d", act);
+  if (act == 0) OG_LAUNCH(0); else if (act == 1) OG_LAUNCH(1); else if (act == 2) OG_LAUNCH(2); else OG_LAUNCH(3);
+#undef OG_LAUNCH
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;

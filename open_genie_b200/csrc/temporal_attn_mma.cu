@@ -1,8 +1,8 @@
-// temporal_attn_mma.cu — EXPERIMENTAL tensor-core form of the temporal (causal, T <= 16, d_head = 64) attention.
+// temporal_attn_mma.cu — tensor-core form of the temporal (causal, T <= 16, d_head = 64) attention.
 //
-// STATUS: compiled for sm_100a and inspected (SASS: LDSM / HMMA.16816.F32.BF16), NOT YET RUN ON HARDWARE — the
-// round's GPU budget ended before it could be validated, so it is OFF by default and reachable only with
-// OG_TEMPORAL_MMA=1. The default path is the validated per-lane kernel pair in attention_rows.cu.
+// STATUS: validated on a B200 in round 2 (tests/test_gpu_attention.py and the full-size LatentAction / Dynamics parity
+// tests) and the default path since then; OG_TEMPORAL_MMA=0 falls back to the per-lane kernels in attention_rows.cu.
+// SASS: LDSM / HMMA.16816.F32.BF16.
 //
 // Why: one (batch, pixel, head) task is a 16 x 16 x 64 score tile and a 16 x 64 x 16 value product. The per-lane
 // dot-product kernels spend ~2.5 K instructions per task and run ~4x above their HBM roofline time; with

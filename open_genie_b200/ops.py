@@ -191,9 +191,12 @@ def mark_step():
         _SCOPE.arena.mark_step()
 
 
-def _zeros(shape, dtype, device):
+def _zeros(shape, dtype, device, recording: bool = False):
+    """Zero-initialised accumulator. Served from the step's arena only while a gradient can exist: inside backward, in
+    grad mode, or — `recording` — inside the forward of an autograd Function that is being recorded (Function.forward
+    itself runs with grad mode off; its ctx.needs_input_grad tells a training forward from a no_grad / inference one)."""
     a = _SCOPE.arena
-    if a is None or not (torch.is_grad_enabled() or _in_backward()):
+    if a is None or not (recording or torch.is_grad_enabled() or _in_backward()):
         return torch.zeros(shape, dtype=dtype, device=device)
     return a.zeros(shape, dtype, device)
 
@@ -538,7 +541,7 @@ class _GroupNormActFn(torch.autograd.Function):
         V = T * H * W
         s = _stream()
         dev = xi.device
-        sums = _zeros((B, G, 2), torch.float64, dev)
+        sums = _zeros((B, G, 2), torch.float64, dev, any(ctx.needs_input_grad))
         _lib.call('og_gn_stats', xi.data_ptr(), B, V, C, G, sums.data_ptr(), s)
         A = torch.empty((B, C), dtype=f32, device=dev)
         Bc = torch.empty((B, C), dtype=f32, device=dev)
@@ -824,6 +827,29 @@ def _rows_bf16(x: Tensor) -> Tensor:
     return x
 
 
+_ROPE_TABLES = {}
+
+
+def _rope_table(freq: Tensor, npos: int) -> Optional[Tensor]:
+    """fp32 (npos, C/2, 2) table of (cos, sin)(pos * freq) for the fused RoPE+LayerNorm passes, cached per frequency
+    vector and sequence length (rebuilt if the `freq` parameter is replaced or modified). Never built while a CUDA
+    graph is being captured: a captured step uses the tables its warm-up steps created, or none."""
+    if _os.environ.get('OG_ROPE_TABLE', '1') == '0':
+        return None
+    key = (freq.data_ptr(), freq._version, int(npos), freq.device)
+    t = _ROPE_TABLES.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        C = 2 * freq.numel()
+        t = torch.empty((npos, C // 2, 2), dtype=f32, device=freq.device)
+        _lib.call('og_rope_table', freq.detach().float().contiguous().data_ptr(), int(npos), C, t.data_ptr(), _stream())
+        if len(_ROPE_TABLES) > 64:
+            _ROPE_TABLES.clear()
+        _ROPE_TABLES[key] = t
+    return t
+
+
 class _SpaceAttnFn(torch.autograd.Function):
     """y = SDPA(q, q, q; scale) + x with q = LayerNorm(RoPE2d(x)), sequences = frames (H*W tokens).
     SpatialAttention.forward + the residual of SpaceTimeAttention.forward (attention.py:279-307, 470)."""
@@ -836,8 +862,9 @@ class _SpaceAttnFn(torch.autograd.Function):
         rows, S = B * T * H * W, H * W
         s = _stream()
         q = torch.empty_like(x)
+        tab = _rope_table(freq, S)
         _lib.call('og_rope_ln_fwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
-                  q.data_ptr(), rows, C, 1, S, s)
+                  q.data_ptr(), rows, C, 1, S, _ptr(tab), s)
         y, o = torch.empty_like(x), torch.empty_like(x)
         lse = torch.empty((B * T, n_head, S), dtype=f32, device=x.device)
         _conv_call('attn_fwd', 4.0 * B * T * S * S * C, 'og_flash_attn_fwd', q.data_ptr(), q.data_ptr(), q.data_ptr(),
@@ -863,7 +890,8 @@ class _SpaceAttnFn(torch.autograd.Function):
         dgamma = _zeros(C, f32, x.device)
         dbeta = _zeros(C, f32, x.device)
         _lib.call('og_rope_ln_bwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), eps, dq.data_ptr(), dk.data_ptr(),
-                  dv.data_ptr(), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, C, 1, S, s)
+                  dv.data_ptr(), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), rows, C, 1, S,
+                  _ptr(_rope_table(freq, S)), s)
         return dx, None, dgamma, dbeta, None, None, None
 
 
@@ -880,7 +908,7 @@ class _TimeAttnFn(torch.autograd.Function):
         s = _stream()
         q = torch.empty_like(x)
         _lib.call('og_rope_ln_fwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps,
-                  q.data_ptr(), B * T * P, C, P, T, s)
+                  q.data_ptr(), B * T * P, C, P, T, _ptr(_rope_table(freq, T)), s)
         y = torch.empty_like(x)
         bcast = k_cond is not None
         if bcast:
@@ -919,7 +947,8 @@ class _TimeAttnFn(torch.autograd.Function):
         dgamma = _zeros(C, f32, x.device)
         dbeta = _zeros(C, f32, x.device)
         _lib.call('og_rope_ln_bwd', x.data_ptr(), freq.data_ptr(), gamma.data_ptr(), eps, dq.data_ptr(), _ptr(g1),
-                  _ptr(g2), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), B * T * P, C, P, T, s)
+                  _ptr(g2), dy.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), B * T * P, C, P, T,
+                  _ptr(_rope_table(freq, T)), s)
         return dx, None, dgamma, dbeta, dkc, dvc, None, None, None
 
 
@@ -935,7 +964,7 @@ class _FfnFn(torch.autograd.Function):
         V = T * H * W
         s = _stream()
         dev = x.device
-        sums = _zeros((B, G, 2), torch.float64, dev)
+        sums = _zeros((B, G, 2), torch.float64, dev, any(ctx.needs_input_grad))
         _lib.call('og_gn_stats', x.data_ptr(), B, V, C, G, sums.data_ptr(), s)
         A = torch.empty((B, C), dtype=f32, device=dev)
         Bc = torch.empty((B, C), dtype=f32, device=dev)
@@ -1121,8 +1150,9 @@ class _ResBlockFn(torch.autograd.Function):
         V = T * H * W
         s = _stream()
         dev = xi.device
+        rec = any(ctx.needs_input_grad)
         if x_sums is None:
-            x_sums = _zeros((B, G, 2), torch.float64, dev)
+            x_sums = _zeros((B, G, 2), torch.float64, dev, rec)
             _lib.call('og_gn_stats', xi.data_ptr(), B, V, C0, G, x_sums.data_ptr(), s)
         mr = torch.empty((2, B, G, 2), dtype=f32, device=dev)
         A1, B1 = torch.empty((B, C0), dtype=f32, device=dev), torch.empty((B, C0), dtype=f32, device=dev)
@@ -1132,7 +1162,7 @@ class _ResBlockFn(torch.autograd.Function):
                   a1.data_ptr(), A1.data_ptr(), B1.data_ptr(), mr[0].data_ptr(), B, V, C0, s)
         ws = _workspace(dev, B * V * C1 * 4)
         fuse_stats = G == 1 and FUSE_STATS
-        sums2 = _zeros((B, G, 2), torch.float64, dev)
+        sums2 = _zeros((B, G, 2), torch.float64, dev, rec)
         h1 = empty_internal(B, C1, T, H, W, bf16, dev)
         _conv_call('fwd', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_fwd', a1.data_ptr(), C0, geom1.kt, geom1.kh,
                    geom1.kw, geom1.pt, geom1.ph, geom1.pw, None, 0, packed1.data_ptr(), packed1.shape[1], _ptr(b1), None,
@@ -1144,7 +1174,7 @@ class _ResBlockFn(torch.autograd.Function):
         _lib.call('og_gn_act_fwd', h1.data_ptr(), sums2.data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, None, eps, G, act,
                   a2.data_ptr(), A2.data_ptr(), B2.data_ptr(), mr[1].data_ptr(), B, V, C1, s)
         y = empty_internal(B, C1, T, H, W, bf16, dev)
-        y_sums = _zeros((B, 1, 2), torch.float64, dev)
+        y_sums = _zeros((B, 1, 2), torch.float64, dev, rec)
         _conv_call('fwd', 2.0 * B * V * C1 * (geom2.k_main + C0), 'og_conv3d_fwd', a2.data_ptr(), C1, geom2.kt, geom2.kh,
                    geom2.kw, geom2.pt, geom2.ph, geom2.pw, xi.data_ptr(), C0, packed2.data_ptr(), packed2.shape[1],
                    _ptr(b2), _ptr(bres), None, y.data_ptr(), 0, B, T, H, W, C1, ws.data_ptr(), ws.numel(),

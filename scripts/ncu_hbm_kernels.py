@@ -44,7 +44,7 @@ freq = torch.rand(Cc // 2, device=dev); g1 = torch.ones(Cc, device=dev, requires
 y = ops.time_attention_res(xa, freq, g1, b1, 4, 4 * 64 ** -0.5)
 y.backward(torch.randn_like(y))
 rows = B * Tt * H * W
-alg['og_rope_ln_fwd_kernel'] = rows * Cc * 4; alg['og_rope_ln_bwd_vec_kernel'] = rows * Cc * 2 * 6
+alg["og_rope_ln_fwd_vec_kernel"] = rows * Cc * 4; alg["og_rope_ln_bwd_vec_kernel"] = rows * Cc * 2 * 6
 alg['og_temporal_attn_fwd_kernel'] = rows * Cc * 2 * 3; alg['og_temporal_attn_bwd_kernel'] = rows * Cc * 2 * 6
 torch.cuda.synchronize()
 print(json.dumps({'algorithmic_bytes_per_launch': alg}))

@@ -17,7 +17,7 @@ def _call(name, *a):
     _lib.call(name, *a, torch.cuda.current_stream().cuda_stream)
 
 
-@pytest.mark.parametrize('kind,C', [('2d', 128), ('1d', 512)])
+@pytest.mark.parametrize('kind,C', [('2d', 128), ('1d', 512), ('2d', 256)])
 def test_rope_layernorm_fwd_bwd(kind, C):
     B, T, H, W = 2, 4, 8, 8
     x = bf16_round(O.det_uniform(f'rl.x.{kind}', (B, T, H, W, C)))
@@ -42,13 +42,25 @@ def test_rope_layernorm_fwd_bwd(kind, C):
     fq, ga, be = freq.to(DEV), gamma.to(DEV), beta.to(DEV)
     rows = B * T * H * W
     _call('og_rope_ln_fwd', xd.data_ptr(), fq.data_ptr(), ga.data_ptr(), be.data_ptr(), 1e-5, y.data_ptr(), rows, C,
-          pos_div, pos_mod)
+          pos_div, pos_mod, None)
     assert_close(y.float(), bf16_round(yo), BF16_ULP, BF16_ULP, 'rope+ln fwd')
+    # the precomputed (cos, sin) table holds the same sincosf values: bit-identical output, forward and backward
+    tab = torch.empty((pos_mod, C // 2, 2), device=DEV)
+    _call('og_rope_table', fq.data_ptr(), pos_mod, C, tab.data_ptr())
+    y_t = torch.empty_like(xd)
+    _call('og_rope_ln_fwd', xd.data_ptr(), fq.data_ptr(), ga.data_ptr(), be.data_ptr(), 1e-5, y_t.data_ptr(), rows, C,
+          pos_div, pos_mod, tab.data_ptr())
+    assert torch.equal(y_t, y), 'table and sincosf paths differ (forward)' 
     g = gy.to(DEV).to(torch.bfloat16).contiguous()
     dx = torch.empty_like(xd)
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     _call('og_rope_ln_bwd', xd.data_ptr(), fq.data_ptr(), ga.data_ptr(), 1e-5, g.data_ptr(), None, None, None,
-          dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C, pos_div, pos_mod)
+          dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, C, pos_div, pos_mod, None)
+    dx_t = torch.empty_like(xd)
+    dg_t, db_t = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    _call('og_rope_ln_bwd', xd.data_ptr(), fq.data_ptr(), ga.data_ptr(), 1e-5, g.data_ptr(), None, None, None,
+          dx_t.data_ptr(), dg_t.data_ptr(), db_t.data_ptr(), rows, C, pos_div, pos_mod, tab.data_ptr())
+    assert torch.equal(dx_t, dx), 'table and sincosf paths differ (backward)' 
     assert_close(dx.float(), xr.grad, 2 * BF16_ULP, 2 * BF16_ULP * xr.grad.abs().max().item(), 'rope+ln dx')
     assert_close(dg, gr.grad, 2e-3, 2e-3 * gr.grad.abs().max().item(), 'dgamma')
     assert_close(db, br.grad, 2e-3, 2e-3 * br.grad.abs().max().item(), 'dbeta')
