@@ -34,6 +34,7 @@ struct WgradParams {
   int a_stages, b_stages;
   int sx_t, sx_h, sx_w;  // X box start = dY box start * stride + tap offset (strided convolution; 1 otherwise)
   int vec_ok;  // dw rows 16-byte aligned: vector reductions
+  int plain_store;  // OG_WGRAD_PLAIN_STORE=1: the ABI says "accumulates", so overwriting is opt-in (the Python side zeroes dw anyway)
   int dbg;     // timing experiments only (OG_WGRAD_DBG): 1 = pretend A is K-major, 2 = pretend B is K-major, 4 = skip epilogue
 };
 
@@ -230,7 +231,14 @@ __global__ void __launch_bounds__(kWThreads, 1)
         tmem_ld_wait();
         if (co < p.cout) {
           float* dst = p.dw + (long long)co * p.ld_dw + (long long)tap * p.cin + ci0 + c;
-          if (p.vec_ok && ci0 + c + 32 <= p.cin) {
+          if (p.vec_ok && ci0 + c + 32 <= p.cin && p.splitk == 1 && p.plain_store) {
+            // one CTA owns this (co, tap, ci) block and the caller's buffer is freshly zeroed: plain vector stores
+            // instead of 32 L2 reductions per thread and chunk (the low-resolution layers run with split-K = 1)
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4)
+              *reinterpret_cast<float4*>(dst + jj) = make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
+                                                                 __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+          } else if (p.vec_ok && ci0 + c + 32 <= p.cin) {
 #pragma unroll
             for (int jj = 0; jj < 32; jj += 4)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + jj), "f"(__uint_as_float(v[jj])),
@@ -311,6 +319,8 @@ static int launch_wgrad(const void* dy, int cout, const void* x, int cin, float*
   {
     const char* e = getenv("OG_WGRAD_DBG");
     p.dbg = e ? atoi(e) : 0;
+    const char* ps = getenv("OG_WGRAD_PLAIN_STORE");
+    p.plain_store = ps ? atoi(ps) : 0;
   }
   p.vec_ok = (ld_dw % 4 == 0) && (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
   const int b_bytes = 2 * (p.block_n / 64) * kPanelBytes;  // a pair of taps per stage
