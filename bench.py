@@ -274,6 +274,10 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # The step needs ~25 GB/s of all-reduce bandwidth (1.5 GB of fp32 gradients per ~65 ms step, overlapped with
+        # backward), while every CTA NCCL occupies takes a whole SM away from the persistent one-CTA-per-SM GEMM kernels
+        # (227 KB of shared memory each: nothing co-resides). Cap NCCL's CTAs; NCCL_MAX_CTAS in the environment wins.
+        os.environ.setdefault('NCCL_MAX_CTAS', os.environ.get('OG_NCCL_MAX_CTAS', '4'))
         dist.init_process_group('nccl', device_id=dev)
 
     import open_genie_b200 as og
@@ -287,7 +291,8 @@ def main():
     opt = model.configure_optimizers()                      # FusedAdamW, AdamW defaults
     og.enable_zero_arena(True)   # every step below ends with zero_grad(set_to_none=True): the arena contract holds
     # N > 1: ONE gradient exchange per step, all-reduced in place on the step's zero arena (no bucket copies)
-    reducer = ArenaGradAllReducer(model.parameters()) if world > 1 else None
+    bucket_mb = int(os.environ.get('OG_BUCKET_MB', '64'))
+    reducer = ArenaGradAllReducer(model.parameters(), bucket_bytes=bucket_mb << 20) if world > 1 else None
     B = args.batch
     torch.manual_seed(1234 + rank)
     host_video = torch.randn(B, 3, FRAMES, RES, RES).pin_memory()
@@ -484,7 +489,7 @@ def main():
                        'params': n_params, 'parallelism': f'dp{world}', 'launch': launch,
                        'grad_exchange': None if reducer is None else
                        f'NCCL all-reduce (AVG) in place on the zero arena, {reducer.bucket >> 20} MB ranges overlapped with '
-                       f'backward, {reducer.grad_bytes()} B per step',
+                       f'backward, {reducer.grad_bytes()} B per step, NCCL_MAX_CTAS={os.environ.get("NCCL_MAX_CTAS")}',
                        'l2': 'no flush: every step streams several GB of activations (>> 126 MB L2)'},
             'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d_bytes * world,
                     'd2h_bytes_per_step': 4 * world,

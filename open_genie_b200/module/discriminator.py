@@ -80,10 +80,48 @@ class FrameDiscriminator(nn.Module):
 
 
 class VideoDiscriminator(nn.Module):
-    """genie/module/discriminator.py:116-221 (`gan_discriminate='video'`): 3-D variant of the critic. Not on the path any
-    shipped configuration takes (config/tokenize.yaml and the VideoTokenizer default use 'frames')."""
+    """genie/module/discriminator.py:116-221 (`gan_discriminate='video'`): the 3-D critic — nn.Conv3d stem, VideoResidualBlocks
+    with LeakyReLU and blur-pool down-sampling, the same x4 Identity quirk, Conv3d + LeakyReLU + Linear head.
+    `use_causal=True` / `use_attn=True` / `use_blur=False` do not construct in the reference either and raise here."""
 
-    def __init__(self, *args, **kwargs) -> None:
+    def __init__(self, inp_size, model_dim: int = 64, dim_mults: Tuple[int, ...] = (1, 2, 4),
+                 down_step=(None, 2, 2), inp_channels: int = 3, kernel_size=3, num_groups: int = 1, num_heads: int = 4,
+                 dim_head: int = 32, act_fn: str = 'leaky', use_attn: bool = False, use_blur: bool = True,
+                 use_causal: bool = False) -> None:
         super().__init__()
-        raise NotImplementedError("VideoDiscriminator (gan_discriminate='video') is outside the B200 hot-path scope; "
-                                  "use gan_discriminate='frames' (the reference default)")
+        if use_attn or use_causal or not use_blur:
+            raise NotImplementedError('VideoDiscriminator: use_attn / use_causal / use_blur=False are outside the scope')
+        from .video import Conv3dParams, VideoResidualBlock
+        inp_size = tuple(inp_size)
+        if len(inp_size) == 2:
+            inp_size = (inp_size[0], inp_size[1], inp_size[1])
+        dims = [model_dim * mult for mult in dim_mults]
+        assert len(dims) == len(down_step), 'Dimension and downsample steps must match.'
+        self.proj_in = Conv3dParams(inp_channels, model_dim, kernel_size, causal=False)
+        self.core = nn.ModuleList([])
+        out_dim = model_dim
+        for (inp_dim, out_dim), down in zip(pairwise(dims), down_step):
+            self.core.append(nn.ModuleList([
+                VideoResidualBlock(inp_dim, out_dim, downsample=down, num_groups=num_groups, kernel_size=kernel_size,
+                                   act_fn=act_fn, use_blur=use_blur, use_causal=use_causal),
+                nn.ModuleList([nn.Identity(), nn.Identity()])]))
+            d = down if down is not None else (1, 1, 1)
+            if isinstance(d, int):
+                d = (d, d, d)
+            if len(d) == 2:
+                d = (d[0], d[1], d[1])
+            inp_size = tuple(x // y for x, y in zip(inp_size, d))
+        latent_dim = out_dim * prod(inp_size)
+        self.to_logits = nn.Sequential(Conv3dParams(out_dim, out_dim, 3, causal=False), nn.Identity(), nn.Identity(),
+                                       _LogitsHead(latent_dim), nn.Identity())
+
+    def forward(self, video: Tensor) -> Tensor:
+        c = self.proj_in
+        out = ops.conv3d(video, c.weight, c.bias, c.packed(), c.geom)
+        for res, _attn in self.core:
+            out = res(out)
+            out = ops.activation(out, 'none', 4.0)        # Identity attn / ff: x + x, twice (discriminator.py:213-218)
+        c = self.to_logits[0]
+        out = ops.conv3d(out, c.weight, c.bias, c.packed(), c.geom)
+        out = ops.activation(out, 'leaky')
+        return self.to_logits[3](out)

@@ -271,8 +271,9 @@ class VideoResidualBlock(nn.Module):
             raise NotImplementedError('VideoResidualBlock(downsample=..., use_blur=False) is not used by any blueprint')
         if use_causal:
             raise NotImplementedError('VideoResidualBlock(use_causal=True) is not used by any shipped blueprint')
-        if act_fn not in ('swish', 'silu') or not use_norm or pad_mode != 'constant':
-            raise NotImplementedError('VideoResidualBlock: only GroupNorm + SiLU blocks are implemented')
+        if act_fn not in ('swish', 'silu', 'leaky', 'relu') or not use_norm or pad_mode != 'constant':
+            raise NotImplementedError('VideoResidualBlock: GroupNorm + SiLU / LeakyReLU / ReLU blocks are implemented')
+        self.act_fn = 'silu' if act_fn == 'swish' else act_fn
         kernel_size = _triple(kernel_size)
         out_channels = default(out_channels, in_channels)
         conv = lambda ci, co, k: Conv3dParams(ci, co, k, causal=use_causal)
@@ -285,7 +286,7 @@ class VideoResidualBlock(nn.Module):
             _GNParams(num_groups, out_channels), _Slot(), conv(out_channels, out_channels, kernel_size),
         )
         self.has_down = exists(downsample)
-        self.main[0].act = self.main[4].act = 'silu'
+        self.main[0].act = self.main[4].act = self.act_fn
         self.main[6].fuse_shortcut(self.res[1])
         self.inp_channels, self.out_channels = in_channels, out_channels
         self.in_channels = in_channels
@@ -305,7 +306,7 @@ class VideoResidualBlock(nn.Module):
             sums = getattr(inp, '_og_gn_sums', None) if g1.num_groups == 1 else None
             y, y_sums = ops.residual_block(inp, sums, g1.weight, g1.bias, c1.weight, c1.bias, g2.weight, g2.bias,
                                            c2.weight, c2.bias, cr.weight, cr.bias, c1.packed(), c2.packed(), c1.geom,
-                                           c2.geom, g1.num_groups, g1.eps)
+                                           c2.geom, g1.num_groups, g1.eps, act=self.act_fn)
             y._og_gn_sums = y_sums
             return y
         h = self.main[0](inp)                # GN + SiLU (fused)

@@ -302,6 +302,15 @@ def gen_gan_perceptual():
     (gen_loss + dis_loss).backward()
     out['gan'] = {'frames_idxs': idxs, 'gen_loss': gen_loss.detach(), 'dis_loss': dis_loss.detach(),
                   'drec': rec.grad.clone(), 'grads': summarize_grads(grads_of(gan))}
+    # the 3-D critic (gan_discriminate='video')
+    from genie.module.discriminator import VideoDiscriminator
+    vd = VideoDiscriminator(inp_size=(8, 32, 32))
+    load_det(vd)
+    clip = O.det_uniform('gan.clip', (2, 3, 8, 32, 32))
+    clip.requires_grad_(True)
+    vs = vd(clip)
+    (-vs.mean()).backward()
+    out['video_disc'] = {'score': vs.detach(), 'dclip': clip.grad.clone(), 'grads': summarize_grads(grads_of(vd))}
     # perceptual loss, closed-form VGG16 feature weights
     perc = PerceptualLoss(model_weights=None, num_frames=k)
     vsd = O.det_state_dict({k_: tuple(v.shape) for k_, v in perc.percept_model.state_dict().items()

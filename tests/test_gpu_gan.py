@@ -43,6 +43,22 @@ def test_frame_discriminator_against_reference(golden):
     _check_grads(_grads(disc), g['grads'], 0.1, 'critic')
 
 
+def test_video_discriminator_against_reference(golden):
+    """gan_discriminate='video': Conv3d stem, LeakyReLU residual blocks with blur-pool down-sampling, Linear head."""
+    from open_genie_b200.module.discriminator import VideoDiscriminator
+    g = golden('gan_perceptual.pt')['video_disc']
+    vd = VideoDiscriminator(inp_size=(8, 32, 32))
+    det_weights(vd)
+    vd.to(DEV)
+    clip = O.det_uniform('gan.clip', (2, 3, 8, 32, 32)).to(DEV).requires_grad_(True)
+    score = vd(clip)
+    assert score.shape == (2,) and score.dtype == torch.float32
+    (-score.mean()).backward()
+    assert_close(score, g['score'], 3e-2, 3e-2 * g['score'].abs().max().item(), 'video critic scores')
+    assert rel_l2(clip.grad.cpu(), g['dclip']) < 0.12
+    _check_grads(_grads(vd), g['grads'], 0.1, 'video critic')
+
+
 def test_gan_hinge_losses_against_reference(golden):
     from open_genie_b200.module.loss import GANLoss
     g = golden('gan_perceptual.pt')['gan']

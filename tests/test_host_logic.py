@@ -58,7 +58,7 @@ def test_state_dict_matches_the_reference(golden):
 
 def test_tokenizer_builds_the_auxiliary_losses_like_the_reference():
     """genie/tokenizer.py:288-299: GANLoss(FrameDiscriminator(**disc_kwargs)) and PerceptualLoss(vgg16) when their
-    weights are > 0 (the constructor defaults), nn.Identity otherwise; the 'video' critic is out of scope."""
+    weights are > 0 (the constructor defaults), nn.Identity otherwise; 'frames' and 'video' critics."""
     import torch.nn as nn
     from open_genie_b200.module.loss import GANLoss, PerceptualLoss
     tok = og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6, disc_kwargs={'inp_size': 32})
@@ -71,8 +71,12 @@ def test_tokenizer_builds_the_auxiliary_losses_like_the_reference():
     assert not any(p.requires_grad for p in tok.perc_crit.parameters())                   # frozen extractor (loss.py:49-51)
     tok0 = og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6, gan_loss_weight=0, perc_loss_weight=0)
     assert isinstance(tok0.gan_crit, nn.Identity) and isinstance(tok0.perc_crit, nn.Identity)
-    with pytest.raises(NotImplementedError, match='VideoDiscriminator'):
-        og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6, gan_discriminate='video', disc_kwargs={'inp_size': (8, 32)})
+    from open_genie_b200.module.discriminator import VideoDiscriminator
+    tokv = og.VideoTokenizer(fx.MINI_ENC, fx.MINI_DEC, d_codebook=6, gan_discriminate='video', perc_loss_weight=0,
+                             disc_kwargs={'inp_size': (8, 32)})
+    assert isinstance(tokv.gan_crit.disc, VideoDiscriminator) and tokv.gan_crit.disc.proj_in.weight.shape == (64, 3, 3, 3, 3)
+    with pytest.raises(NotImplementedError, match='use_attn'):
+        VideoDiscriminator(inp_size=(8, 32), use_attn=True)
 
 
 def test_conv_geometry():
