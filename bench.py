@@ -274,10 +274,12 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # The step needs ~25 GB/s of all-reduce bandwidth (1.5 GB of fp32 gradients per ~65 ms step, overlapped with
-        # backward), while every CTA NCCL occupies takes a whole SM away from the persistent one-CTA-per-SM GEMM kernels
-        # (227 KB of shared memory each: nothing co-resides). Cap NCCL's CTAs; NCCL_MAX_CTAS in the environment wins.
-        os.environ.setdefault('NCCL_MAX_CTAS', os.environ.get('OG_NCCL_MAX_CTAS', '4'))
+        # Every CTA NCCL occupies takes a whole SM away from the persistent one-CTA-per-SM GEMM kernels (227 KB of shared
+        # memory each: nothing co-resides); capping NCCL's CTAs was measured and is WORSE (N = 2, profiles/r02j_*: 8 CTAs
+        # 66.3 ms = default, 4 CTAs 69.7, 2 CTAs 81.3 — the all-reduce then no longer hides behind backward). The GEMM
+        # kernels instead draw their tiles dynamically, so CTAs that cannot be resident cost nothing (conv3d_igemm.cu).
+        if os.environ.get('OG_NCCL_MAX_CTAS'):
+            os.environ.setdefault('NCCL_MAX_CTAS', os.environ['OG_NCCL_MAX_CTAS'])
         dist.init_process_group('nccl', device_id=dev)
 
     import open_genie_b200 as og
@@ -293,6 +295,10 @@ def main():
     # N > 1: ONE gradient exchange per step, all-reduced in place on the step's zero arena (no bucket copies)
     bucket_mb = int(os.environ.get('OG_BUCKET_MB', '64'))
     reducer = ArenaGradAllReducer(model.parameters(), bucket_bytes=bucket_mb << 20) if world > 1 else None
+    if os.environ.get('OG_DDP_MODE') == 'none':     # diagnosis only: N independent replicas, no gradient exchange
+        for h in reducer._hooks:
+            h.remove()
+        reducer = None
     B = args.batch
     torch.manual_seed(1234 + rank)
     host_video = torch.randn(B, 3, FRAMES, RES, RES).pin_memory()
@@ -462,7 +468,7 @@ def main():
         if dom:
             traffic, traffic_note = None, None
             try:    # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
-                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')))[dom]
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))[dom]
                 traffic = tj['traffic_bytes']
                 traffic_note = (f"ncu --set full, one launch of {tj['shape']}: dram read {tj['dram_read_bytes']} + "
                                 f"write {tj['dram_write_bytes']} B; algorithmic {tj['algorithmic_bytes']} B")

@@ -67,6 +67,12 @@ uint64_t og_launch_count(void);
  * gn_sums (optional): fp64 [N][2] += (sum, sum of squares) of the bf16 output per sample — the og_gn_stats
  * result for a following GroupNorm(1, C) — produced in the GEMM epilogue when the tiling allows it, otherwise
  * by an internal og_gn_stats pass; either way the caller just zeroes it first. */
+/* workspace protocol (og_conv3d_fwd / og_conv3d_dgrad): the last 256 bytes of a workspace prepared with og_workspace_init
+ * hold a self-resetting tile counter — the persistent GEMM CTAs then draw their tiles dynamically, so a launch that shares
+ * the GPU with another kernel (the NCCL all-reduce of the data-parallel step) does not wait for CTAs that could not become
+ * resident. An unprepared workspace (or NULL) gets the static round-robin tile assignment; results are identical. */
+int og_workspace_init(void* workspace, size_t workspace_bytes, og_stream_t stream);
+
 int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1, int c1,
                   const void* w, int ldw, const float* bias0, const float* bias1, const void* residual, void* out,
                   int out_f32, int N, int T, int H, int W, int cout, void* workspace, size_t workspace_bytes,
@@ -152,6 +158,17 @@ int og_gn_bwd_finalize(const float* S, const float* mean_rstd, const float* gamm
 int og_affine_act_bwd_apply(const void* dy, const void* x, const float* A, const float* B, const float* Q,
                             const float* R, const void* add, void* dx, int act, int N, int64_t V, int C,
                             og_stream_t stream);
+
+/* AdaptiveGroupNorm conditioning (genie/module/norm.py:58-66): cbar = mean over (t,h,w) of cond [N][V][D] (fp32,
+ * channels-last rows), scale = w_scale cbar + b_scale, shift = w_shift cbar + b_shift (the two nn.Linear(dim_cond, C)),
+ * all in one launch; the backward launch writes (does not accumulate) dw_* [C][D], db_* [C] and, if dcond != NULL,
+ * dcond [N][V][D] = (dscale w_scale + dshift w_shift) / V broadcast over the voxels. D <= 64. */
+int og_adagn_cond_fwd(const float* cond, int N, int64_t V, int D, const float* w_scale, const float* b_scale,
+                      const float* w_shift, const float* b_shift, int C, float* cbar, float* scale, float* shift,
+                      og_stream_t stream);
+int og_adagn_cond_bwd(const float* dscale, const float* dshift, const float* cbar, const float* w_scale,
+                      const float* w_shift, int N, int64_t V, int D, int C, float* dw_scale, float* db_scale,
+                      float* dw_shift, float* db_shift, float* dcond, og_stream_t stream);
 
 /* One-launch forms of the two pairs above, used on the training hot path (same math, same outputs):
  * og_gn_act_fwd  = og_gn_finalize + og_affine_act_fwd  (A, B, mean_rstd are still written for backward);

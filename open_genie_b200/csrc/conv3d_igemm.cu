@@ -73,6 +73,7 @@ struct IgemmParams {
   float* red_S;                // ... S[n][c] += (sum dpre, sum dpre*x), dpre = d * act'(x*A+B)   (og_affine_act_bwd_reduce)
   int red_act;
   int swap;        // operand swap (see below): D^T[cout][256 voxels] = W . X^T, used when Cout tiles are 128 wide
+  unsigned int* sched;  // dynamic tile scheduler state {magic, next item, CTAs done} in the caller's workspace, or NULL
   int splits;      // split-K factor (1 = none): each work item covers a k-block range and reduces into `ws`
   float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zeroed by the launcher) when splits > 1
 };
@@ -84,6 +85,8 @@ static constexpr int kTmemCols = 512;
 static constexpr int kAccStride = 256;                   // columns between the two accumulator buffers
 static constexpr int kMaxStages = 8;
 static constexpr int kThreads = 192;
+static constexpr int kSchedDepth = 4;
+static constexpr unsigned int kSchedMagic = 0x0695CED0u;   // written by og_workspace_init
 
 struct TileCoord {
   int n0, t0, h0, w0;
@@ -120,6 +123,15 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  // Dynamic tile scheduler (round 2). With the static `item = blockIdx.x + i * gridDim.x` assignment a CTA that cannot be
+  // resident (another kernel — the NCCL all-reduce of the data-parallel step — holds its SM; this kernel's 227 KB of
+  // shared memory exclude co-residency) starts only when a sibling CTA finishes and then still owns its full share of
+  // tiles: the launch takes ~2x as long. Here the producer warp draws work items from a global counter and hands them to
+  // the MMA / epilogue warps through a 4-deep shared-memory ring, so late CTAs simply find no work left.
+  uint64_t* sched_full = bars + 2 * kMaxStages + 5;    // [4]
+  uint64_t* sched_empty = bars + 2 * kMaxStages + 9;   // [4]
+  int* sched_item = reinterpret_cast<int*>(bars + 2 * kMaxStages + 13);  // [4]
+  const bool dyn = p.sched != nullptr && p.sched[0] == kSchedMagic;
   float* bias_s = reinterpret_cast<float*>(bars + 32);                    // [256] bias0+bias1 of the current N tile
   uint8_t* stage_s = reinterpret_cast<uint8_t*>(bars + 32) + 1024;        // 4 warps x 32 rows x 128 B store staging
   float* coef_s = reinterpret_cast<float*>(stage_s + 4 * 4096);          // [2][256] A, B of the current sample / N tile
@@ -143,6 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);
     }
+    for (int a = 0; a < kSchedDepth; ++a) {
+      mbar_init(&sched_full[a], 1);
+      mbar_init(&sched_empty[a], 5);   // MMA warp + 4 epilogue warps
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -157,7 +173,28 @@ __global__ void __launch_bounds__(kThreads, 1)
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+      int sslot = 0;
+      uint32_t sphase = 0;
+      for (int iter = 0;; ++iter) {
+        int item;
+        if (dyn) {
+          mbar_wait(&sched_empty[sslot], sphase ^ 1);
+          int got = 0;
+          if (elect_one()) got = (int)atomicAdd(p.sched + 1, 1u);
+          item = __reduce_max_sync(0xffffffffu, got);          // broadcast (items are >= 0)
+          if (elect_one()) {
+            sched_item[sslot] = item;
+            mbar_arrive(&sched_full[sslot]);                    // release: the slot is visible to the waiters
+          }
+          __syncwarp();
+          if (++sslot == kSchedDepth) {
+            sslot = 0;
+            sphase ^= 1;
+          }
+        } else {
+          item = blockIdx.x + iter * gridDim.x;
+        }
+        if (item >= total_tiles) break;
         const int tile = item / p.splits, split = item - tile * p.splits;
         const int m_super = tile / p.num_n_tiles;
         const int n_tile = tile - m_super * p.num_n_tiles;
@@ -225,6 +262,16 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
     __syncwarp();
+    if (dyn && elect_one()) {
+      // last CTA to finish resets the counter for the next launch that uses this workspace (stream-ordered)
+      __threadfence();
+      const unsigned int old = atomicInc(p.sched + 2, gridDim.x - 1);
+      if (old == gridDim.x - 1) {
+        __threadfence();
+        p.sched[1] = 0u;
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     {
@@ -234,7 +281,23 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+      int sslot = 0;
+      uint32_t sphase = 0;
+      for (int iter = 0;; ++iter) {
+        int item;
+        if (dyn) {
+          mbar_wait(&sched_full[sslot], sphase);
+          item = sched_item[sslot];
+          __syncwarp();
+          if (elect_one()) mbar_arrive(&sched_empty[sslot]);
+          if (++sslot == kSchedDepth) {
+            sslot = 0;
+            sphase ^= 1;
+          }
+        } else {
+          item = blockIdx.x + iter * gridDim.x;
+        }
+        if (item >= total_tiles) break;
         const int split = item % p.splits;
         const int nkb = (int)(((long long)p.num_kb * (split + 1)) / p.splits) -
                         (int)(((long long)p.num_kb * split) / p.splits);
@@ -303,7 +366,23 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int j = threadIdx.x - 64; j < 512; j += 128) red_s[j] = 0.f;
     if (threadIdx.x == 64) stat_s[0] = stat_s[1] = 0.0;
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+    int sslot = 0;
+    uint32_t sphase = 0;
+    for (int iter = 0;; ++iter) {
+      int item;
+      if (dyn) {
+        mbar_wait_relaxed(&sched_full[sslot], sphase);
+        item = sched_item[sslot];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sched_empty[sslot]);
+        if (++sslot == kSchedDepth) {
+          sslot = 0;
+          sphase ^= 1;
+        }
+      } else {
+        item = blockIdx.x + iter * gridDim.x;
+      }
+      if (item >= total_tiles) break;
       const int tile = item / p.splits;
       const int m_super = tile / p.num_n_tiles;
       const int n_tile = tile - m_super * p.num_n_tiles;
@@ -786,13 +865,25 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   }
   const int stage_bytes = p.m_sub * kABytes + p.block_n * kBlockK * 2;
   p.fast_store = (!L.out_f32 && n_out % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
+  // dynamic tile scheduling: state lives in the last 256 bytes of the caller's workspace (og_workspace_init)
+  p.sched = nullptr;
+  size_t ws_usable = L.workspace_bytes;
+  if (L.workspace && L.workspace_bytes >= 4096) {
+    const size_t off = (L.workspace_bytes - 256) & ~(size_t)255;
+    ws_usable = off;
+    static const bool dyn_on = [] {
+      const char* e = getenv("OG_IGEMM_DYNAMIC");
+      return !(e && atoi(e) == 0);
+    }();
+    if (dyn_on) p.sched = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(L.workspace) + off);
+  }
   // split-K when the tiles cannot fill the machine and each has a long K loop
   p.splits = 1;
   p.ws = nullptr;
   if (plain) {
     const long long tiles = (long long)((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles;
     const size_t need = (size_t)N * T * H * W * n_out * sizeof(float);
-    if (tiles * 2 <= num_sms() && p.num_kb >= 32 && L.workspace && L.workspace_bytes >= need && !L.residual) {
+    if (tiles * 2 <= num_sms() && p.num_kb >= 32 && L.workspace && ws_usable >= need && !L.residual) {
       int sp = (int)(num_sms() / tiles);
       if (sp > p.num_kb / 8) sp = p.num_kb / 8;
       if (sp > 16) sp = 16;
@@ -952,6 +1043,20 @@ extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void*
   L.workspace = workspace; L.workspace_bytes = workspace_bytes;
   L.red_x = red_x; L.red_A = red_A; L.red_B = red_B; L.red_act = red_act; L.red_S = red_S;
   return launch_igemm(L, (cudaStream_t)stream);
+}
+
+// Prepares a workspace for og_conv3d_fwd / og_conv3d_dgrad: writes the dynamic tile scheduler's state {magic, 0, 0} into
+// its last 256 bytes. Call once after allocating (or re-allocating) the buffer; the kernels reset the state themselves.
+// A workspace that was not initialised (no magic) simply gets the static tile assignment.
+extern "C" int og_workspace_init(void* workspace, size_t workspace_bytes, og_stream_t stream) {
+  using namespace og;
+  OG_REQUIRE(workspace && workspace_bytes >= 4096, "workspace_init: need a workspace of at least 4096 bytes");
+  const size_t off = (workspace_bytes - 256) & ~(size_t)255;
+  char* tail = reinterpret_cast<char*>(workspace) + off;
+  OG_CHECK_CUDA(cudaMemsetAsync(tail, 0, 256, (cudaStream_t)stream));
+  static const unsigned int magic = kSchedMagic;
+  OG_CHECK_CUDA(cudaMemcpyAsync(tail, &magic, sizeof(magic), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return OG_OK;
 }
 
 static int out_extent(int in, int pad_front, int pad_back, int k, int s) { return (in + pad_front + pad_back - k) / s + 1; }

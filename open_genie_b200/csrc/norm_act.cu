@@ -607,6 +607,104 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// AdaptiveGroupNorm conditioning (genie/module/norm.py:58-66): cbar = mean_{t,h,w}(cond); scale = W_s cbar + b_s;
+// shift = W_a cbar + b_a. One block per sample; replaces a mean reduction, two GEMVs and their bias adds (and, backward,
+// two GEMVs, two outer products and two bias reductions) that used to run as ~10 small library launches per layer.
+// cond: fp32 rows [N][V][D] (channels-last), D <= 64.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    og_adagn_cond_fwd_kernel(const float* __restrict__ cond, long long V, int D, const float* __restrict__ Ws,
+                             const float* __restrict__ bs, const float* __restrict__ Wa, const float* __restrict__ ba,
+                             int C, float* __restrict__ cbar, float* __restrict__ scale, float* __restrict__ shift) {
+  const int n = blockIdx.x;
+  __shared__ float part[256];
+  __shared__ float cb[64];
+  const float* cp = cond + (long long)n * V * D;
+  // thread t owns channel d = t % D of rows t / D, t / D + 256 / D ... (coalesced: consecutive threads, consecutive floats)
+  const int per = 256 / D;                 // row lanes
+  const int d = threadIdx.x % D, rl = threadIdx.x / D;
+  float a = 0.f;
+  if (rl < per)
+    for (long long r = rl; r < V; r += per) a += cp[r * D + d];
+  part[threadIdx.x] = rl < per ? a : 0.f;
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float t = 0.f;
+    for (int l = 0; l < per; ++l) t += part[l * D + threadIdx.x];
+    t /= (float)V;
+    cb[threadIdx.x] = t;
+    cbar[n * D + threadIdx.x] = t;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = bs ? bs[c] : 0.f, h = ba ? ba[c] : 0.f;
+    for (int k = 0; k < D; ++k) {
+      s = fmaf(Ws[c * D + k], cb[k], s);
+      if (Wa) h = fmaf(Wa[c * D + k], cb[k], h);
+    }
+    scale[(long long)n * C + c] = s;
+    if (shift) shift[(long long)n * C + c] = h;
+  }
+}
+
+// backward, one launch: block b < D_blocks ... simple form: grid (C/64 + 1): blocks [0, C/64) own 64 output channels each and
+// write dWs, dbs, dWa, dba for them (sum over the N samples, no atomics); the last block writes dcbar and broadcasts it.
+__global__ void __launch_bounds__(256)
+    og_adagn_cond_bwd_kernel(const float* __restrict__ dscale, const float* __restrict__ dshift,
+                             const float* __restrict__ cbar, const float* __restrict__ Ws, const float* __restrict__ Wa,
+                             int N, long long V, int D, int C, float* __restrict__ dWs, float* __restrict__ dbs,
+                             float* __restrict__ dWa, float* __restrict__ dba, float* __restrict__ dcond) {
+  const int cblocks = (C + 63) / 64;
+  if ((int)blockIdx.x < cblocks) {
+    // (c, k) pairs of this block: 64 channels x D
+    for (int i = threadIdx.x; i < 64 * D; i += 256) {
+      const int c = blockIdx.x * 64 + i / D, k = i % D;
+      if (c >= C) continue;
+      float gs = 0.f, ga = 0.f;
+      for (int n = 0; n < N; ++n) {
+        const float cb = cbar[n * D + k];
+        gs = fmaf(dscale[(long long)n * C + c], cb, gs);
+        if (dshift) ga = fmaf(dshift[(long long)n * C + c], cb, ga);
+      }
+      dWs[c * D + k] = gs;
+      if (dWa) dWa[c * D + k] = ga;
+    }
+    for (int i = threadIdx.x; i < 64; i += 256) {
+      const int c = blockIdx.x * 64 + i;
+      if (c >= C) continue;
+      float gs = 0.f, ga = 0.f;
+      for (int n = 0; n < N; ++n) {
+        gs += dscale[(long long)n * C + c];
+        if (dshift) ga += dshift[(long long)n * C + c];
+      }
+      if (dbs) dbs[c] = gs;
+      if (dba) dba[c] = ga;
+    }
+    return;
+  }
+  if (!dcond) return;
+  // dcbar[n][k] = sum_c dscale[n][c] Ws[c][k] + dshift[n][c] Wa[c][k];  dcond[n][v][k] = dcbar[n][k] / V
+  __shared__ float dcb[64];
+  for (int n = 0; n < N; ++n) {
+    __syncthreads();
+    // warp w reduces k = w, w + 8, ...
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < D; k += 8) {
+      float a = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        a = fmaf(dscale[(long long)n * C + c], Ws[c * D + k], a);
+        if (dshift && Wa) a = fmaf(dshift[(long long)n * C + c], Wa[c * D + k], a);
+      }
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) dcb[k] = a / (float)V;
+    }
+    __syncthreads();
+    float* dp = dcond + (long long)n * V * D;
+    for (long long i = threadIdx.x; i < V * D; i += 256) dp[i] = dcb[i % D];
+  }
+}
+
 // (blocks_per_sample, N) grid of ~per_sm blocks per SM; every block owns a contiguous range of whole
 // kStatRows-row groups of one sample.
 static dim3 reduce_grid(int N, long long V, long long* rows_per_block, int per_sm = 4) {
@@ -756,6 +854,32 @@ extern "C" int og_gn_act_bwd(const void* dy, const void* x, const float* A, cons
   OG_REQUIRE(act >= 0 && act <= 3, "gn_act_bwd: unknown activation code %d", act);
   if (act == 0) OG_LAUNCH(0); else if (act == 1) OG_LAUNCH(1); else if (act == 2) OG_LAUNCH(2); else OG_LAUNCH(3);
 #undef OG_LAUNCH
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_adagn_cond_fwd(const float* cond, int N, int64_t V, int D, const float* w_scale, const float* b_scale,
+                                 const float* w_shift, const float* b_shift, int C, float* cbar, float* scale, float* shift,
+                                 og_stream_t stream) {
+  OG_REQUIRE(cond && w_scale && cbar && scale && N > 0 && V > 0, "adagn_cond_fwd: bad arguments");
+  OG_REQUIRE(D >= 1 && D <= 64 && C >= 1, "adagn_cond_fwd: dim_cond=%d must be in [1, 64]", D);
+  OG_REQUIRE((w_shift != nullptr) == (shift != nullptr), "adagn_cond_fwd: w_shift and shift go together");
+  og_adagn_cond_fwd_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(cond, V, D, w_scale, b_scale, w_shift, b_shift, C, cbar,
+                                                               scale, shift);
+  OG_CHECK_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return OG_OK;
+}
+
+extern "C" int og_adagn_cond_bwd(const float* dscale, const float* dshift, const float* cbar, const float* w_scale,
+                                 const float* w_shift, int N, int64_t V, int D, int C, float* dw_scale, float* db_scale,
+                                 float* dw_shift, float* db_shift, float* dcond, og_stream_t stream) {
+  OG_REQUIRE(dscale && cbar && w_scale && dw_scale && N > 0 && V > 0, "adagn_cond_bwd: bad arguments");
+  OG_REQUIRE(D >= 1 && D <= 64 && C >= 1, "adagn_cond_bwd: dim_cond=%d must be in [1, 64]", D);
+  const int blocks = (C + 63) / 64 + 1;
+  og_adagn_cond_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dscale, dshift, cbar, w_scale, w_shift, N, V, D, C,
+                                                                    dw_scale, db_scale, dw_shift, db_shift, dcond);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return OG_OK;

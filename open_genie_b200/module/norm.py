@@ -27,8 +27,9 @@ class AdaptiveGroupNorm(nn.Module):
     """GN(x) * Linear(mean(cond)) + Linear(mean(cond)) — genie/module/norm.py:8-69.
     state_dict keys: weight, bias, std.{weight,bias}, avg.{weight,bias}; same init (norm.py:43-53).
 
-    The (B, dim_cond) -> (B, C) projections are a few kFLOP of host-side plumbing (torch, autograd); the
-    modulation itself is folded into the same per-(sample, channel) scale/shift pass as the GroupNorm."""
+    The conditioning path (mean over the latent grid, two (B, dim_cond) -> (B, C) projections) is one fused kernel each way
+    (ops.adagn_condition); the modulation itself is folded into the same per-(sample, channel) scale/shift pass as the
+    GroupNorm."""
 
     def __init__(self, dim_cond: int, num_groups: int, num_channels: int, cond_bias: bool = True, affine: bool = True,
                  eps: float = 1e-5, device=None, dtype=None) -> None:
@@ -52,7 +53,8 @@ class AdaptiveGroupNorm(nn.Module):
             nn.init.zeros_(self.avg.weight)
 
     def forward(self, inp: Tensor, cond: Tensor) -> Tensor:
-        c = cond.flatten(2).float().mean(-1)                       # 'b d ... -> b d (...)' .mean(-1)   (norm.py:62)
-        std = self.std(c)
-        avg = self.avg(c) if self.avg is not None else None
+        # 'b d ... -> b d (...)' .mean(-1), then the two Linear(dim_cond, C)  (norm.py:62-66): one fused launch
+        std, avg = ops.adagn_condition(cond, self.std.weight, self.std.bias,
+                                       self.avg.weight if self.avg is not None else None,
+                                       self.avg.bias if self.avg is not None else None)
         return ops.group_norm_act(inp, self.weight, self.bias, self.num_groups, self.eps, 'none', std, avg)

@@ -144,7 +144,9 @@ class StepScope:
         if t is None or t.numel() < nbytes:
             if self.frozen or (dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()):
                 raise RuntimeError('open_genie_b200: split-K workspace of a captured training step would have to grow')
-            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            t = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+            if dev.type == 'cuda':      # dynamic tile scheduler state in the buffer's tail (include/opengenie_b200.h)
+                _lib.call('og_workspace_init', t.data_ptr(), t.numel(), torch.cuda.current_stream(dev).cuda_stream)
             self.ws[dev] = t
         return t
 
@@ -608,6 +610,54 @@ def act_code(act) -> int:
 
 def group_norm_act(x, gamma, beta, num_groups, eps=1e-5, act='none', cond_scale=None, cond_shift=None):
     return _GroupNormActFn.apply(x, gamma, beta, cond_scale, cond_shift, num_groups, eps, act_code(act))
+
+
+class _AdaGNCondFn(torch.autograd.Function):
+    """(scale, shift) = (W_s cbar + b_s, W_a cbar + b_a), cbar = mean_{t,h,w}(cond) — AdaptiveGroupNorm.forward's
+    conditioning path (genie/module/norm.py:58-66) in one launch each way (og_adagn_cond_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, cond, w_s, b_s, w_a, b_a):
+        _require_cuda(cond, 'AdaGN condition')
+        B, D = cond.shape[0], cond.shape[1]
+        rows = cond.detach().movedim(1, -1)                       # (B, ..., D): free for channels-last conditions
+        if rows.dtype != f32 or not rows.is_contiguous():
+            rows = rows.to(f32).contiguous()
+        V = rows.numel() // (B * D)
+        C = w_s.shape[0]
+        dev = cond.device
+        cbar = torch.empty((B, D), dtype=f32, device=dev)
+        scale = torch.empty((B, C), dtype=f32, device=dev)
+        shift = torch.empty((B, C), dtype=f32, device=dev) if w_a is not None else None
+        _lib.call('og_adagn_cond_fwd', rows.data_ptr(), B, V, D, w_s.data_ptr(), _ptr(b_s), _ptr(w_a), _ptr(b_a), C,
+                  cbar.data_ptr(), scale.data_ptr(), _ptr(shift), _stream())
+        ctx.cfg = (tuple(cond.shape), V, w_a is not None)
+        ctx.save_for_backward(cbar, w_s, w_a)
+        return scale, shift
+
+    @staticmethod
+    def backward(ctx, dscale, dshift):
+        cbar, w_s, w_a = ctx.saved_tensors
+        shape, V, has_shift = ctx.cfg
+        B, D = shape[0], shape[1]
+        C = w_s.shape[0]
+        dev = cbar.device
+        ds = dscale.detach().to(f32).contiguous()
+        dh = dshift.detach().to(f32).contiguous() if (has_shift and dshift is not None) else None
+        dws = torch.empty_like(w_s, dtype=f32)
+        dbs = torch.empty((C,), dtype=f32, device=dev)
+        dwa = torch.empty_like(w_a, dtype=f32) if has_shift else None
+        dba = torch.empty((C,), dtype=f32, device=dev) if has_shift else None
+        dcond = None
+        if ctx.needs_input_grad[0]:
+            dcond = torch.empty((B,) + tuple(shape[2:]) + (D,), dtype=f32, device=dev)
+        _lib.call('og_adagn_cond_bwd', ds.data_ptr(), _ptr(dh), cbar.data_ptr(), w_s.data_ptr(), _ptr(w_a), B, V, D, C,
+                  dws.data_ptr(), dbs.data_ptr(), _ptr(dwa), _ptr(dba), _ptr(dcond), _stream())
+        return (dcond.movedim(-1, 1) if dcond is not None else None), dws, dbs, dwa, dba
+
+
+def adagn_condition(cond, w_scale, b_scale, w_shift=None, b_shift=None):
+    return _AdaGNCondFn.apply(cond, w_scale, b_scale, w_shift, b_shift)
 
 
 class _ActFn(torch.autograd.Function):

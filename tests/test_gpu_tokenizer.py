@@ -111,6 +111,47 @@ def test_fused_adamw_matches_torch():
         assert_close(x, y, 1e-5, 1e-6, 'adamw')
 
 
+def test_fused_adamw_closure_state_dict_and_lr_schedule():
+    """step(closure) must run the closure with grad enabled (Lightning's automatic optimisation); the step
+    count must survive state_dict()/load_state_dict() in torch.optim.AdamW's layout; a changed learning rate must reach
+    the kernel (device scalar), also under a captured graph."""
+    from open_genie_b200.module.video import CausalConv3d
+    from open_genie_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    m = CausalConv3d(64, 64, 3).to(DEV)
+    x = torch.randn(1, 64, 2, 8, 8, device=DEV)
+    opt = FusedAdamW(m.parameters(), lr=1e-4)
+
+    def closure():
+        opt.zero_grad(set_to_none=True)
+        loss = m(x).float().square().mean()
+        loss.backward()                       # needs grad mode inside step()
+        return loss
+    l0 = opt.step(closure)
+    l1 = opt.step(closure)
+    assert l1.item() < l0.item() and opt.step_count() == 2
+    sd = opt.state_dict()
+    steps = [float(st['step']) for st in sd['state'].values()]
+    assert steps and all(s == 2.0 for s in steps) and all({'exp_avg', 'exp_avg_sq', 'step'} <= set(st) for st in sd['state'].values())
+    # a torch AdamW accepts the checkpoint (interchangeable layout), and a fresh FusedAdamW resumes at step 2
+    ref = torch.optim.AdamW(m.parameters(), lr=1e-4)
+    ref.load_state_dict(sd)
+    opt2 = FusedAdamW(m.parameters(), lr=1e-4)
+    opt2.load_state_dict(sd)
+    opt2.step(closure)
+    assert opt2.step_count() == 3
+    # learning-rate changes reach the kernel: with lr = 0 (and no weight decay term left) the weights stay put
+    w = m.conv3d.weight.detach().clone()
+    for g in opt2.param_groups:
+        g['lr'] = 0.0
+    opt2.step(closure)
+    assert torch.equal(w, m.conv3d.weight.detach())
+    for g in opt2.param_groups:
+        g['lr'] = 1e-4
+    opt2.step(closure)
+    assert not torch.equal(w, m.conv3d.weight.detach())
+
+
 def test_fused_adamw_refreshes_packed_conv_operand():
     from open_genie_b200.module.video import CausalConv3d
     from open_genie_b200.optim import FusedAdamW
