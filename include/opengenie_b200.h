@@ -68,9 +68,10 @@ uint64_t og_launch_count(void);
  * result for a following GroupNorm(1, C) — produced in the GEMM epilogue when the tiling allows it, otherwise
  * by an internal og_gn_stats pass; either way the caller just zeroes it first. */
 /* workspace protocol (og_conv3d_fwd / og_conv3d_dgrad): the last 256 bytes of a workspace prepared with og_workspace_init
- * hold a self-resetting tile counter — the persistent GEMM CTAs then draw their tiles dynamically, so a launch that shares
- * the GPU with another kernel (the NCCL all-reduce of the data-parallel step) does not wait for CTAs that could not become
- * resident. An unprepared workspace (or NULL) gets the static round-robin tile assignment; results are identical. */
+ * hold a self-resetting tile counter. With OG_IGEMM_DYNAMIC=1 in the environment the persistent GEMM CTAs draw their tiles
+ * from it dynamically, so a launch that shares the GPU with another kernel does not wait for CTAs that could not become
+ * resident (an experiment of round 2: no measurable gain, hence opt-in). Otherwise, or with an unprepared / NULL
+ * workspace, tiles are assigned round-robin; results are identical. */
 int og_workspace_init(void* workspace, size_t workspace_bytes, og_stream_t stream);
 
 int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1, int c1,

@@ -871,9 +871,12 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (L.workspace && L.workspace_bytes >= 4096) {
     const size_t off = (L.workspace_bytes - 256) & ~(size_t)255;
     ws_usable = off;
+    // OFF by default: measured on 2 x B200 (profiles/r02k_*), the graphed data-parallel step takes 68.7 ms with either
+    // assignment and the single-GPU step is within noise (64.9 dynamic vs 64.6 static) — the cost of overlapping the
+    // all-reduce turned out to be power, not SM residency. OG_IGEMM_DYNAMIC=1 enables it.
     static const bool dyn_on = [] {
       const char* e = getenv("OG_IGEMM_DYNAMIC");
-      return !(e && atoi(e) == 0);
+      return e && atoi(e) == 1;
     }();
     if (dyn_on) p.sched = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(L.workspace) + off);
   }
