@@ -648,8 +648,8 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// backward, one launch: block b < D_blocks ... simple form: grid (C/64 + 1): blocks [0, C/64) own 64 output channels each and
-// write dWs, dbs, dWa, dba for them (sum over the N samples, no atomics); the last block writes dcbar and broadcasts it.
+// backward, one launch: grid (C/64 + N): blocks [0, C/64) own 64 output channels each and write dWs, dbs, dWa, dba for
+// them (sum over the N samples, no atomics); block C/64 + n writes dcbar of sample n and broadcasts it over the voxels.
 __global__ void __launch_bounds__(256)
     og_adagn_cond_bwd_kernel(const float* __restrict__ dscale, const float* __restrict__ dshift,
                              const float* __restrict__ cbar, const float* __restrict__ Ws, const float* __restrict__ Wa,
@@ -684,10 +684,10 @@ __global__ void __launch_bounds__(256)
     return;
   }
   if (!dcond) return;
-  // dcbar[n][k] = sum_c dscale[n][c] Ws[c][k] + dshift[n][c] Wa[c][k];  dcond[n][v][k] = dcbar[n][k] / V
+  // dcbar[n][k] = sum_c dscale[n][c] Ws[c][k] + dshift[n][c] Wa[c][k];  dcond[n][v][k] = dcbar[n][k] / V   (one block per n)
   __shared__ float dcb[64];
-  for (int n = 0; n < N; ++n) {
-    __syncthreads();
+  {
+    const int n = (int)blockIdx.x - cblocks;
     // warp w reduces k = w, w + 8, ...
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = warp; k < D; k += 8) {
@@ -877,7 +877,7 @@ extern "C" int og_adagn_cond_bwd(const float* dscale, const float* dshift, const
                                  float* dw_shift, float* db_shift, float* dcond, og_stream_t stream) {
   OG_REQUIRE(dscale && cbar && w_scale && dw_scale && N > 0 && V > 0, "adagn_cond_bwd: bad arguments");
   OG_REQUIRE(D >= 1 && D <= 64 && C >= 1, "adagn_cond_bwd: dim_cond=%d must be in [1, 64]", D);
-  const int blocks = (C + 63) / 64 + 1;
+  const int blocks = (C + 63) / 64 + (dcond ? N : 0);
   og_adagn_cond_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dscale, dshift, cbar, w_scale, w_shift, N, V, D, C,
                                                                     dw_scale, db_scale, dw_shift, db_shift, dcond);
   OG_CHECK_CUDA(cudaGetLastError());

@@ -1234,6 +1234,7 @@ class _ResBlockFn(torch.autograd.Function):
         ctx.cfg = (geom1, geom2, G, b1 is not None, b2 is not None, bres is not None, act)
         ctx.save_for_backward(xi, a1, h1, a2, A1, B1, A2, B2, mr, g1w, g1b, g2w, g2b, packed1, packed2)
         ctx.mark_non_differentiable(y_sums)
+        ctx.set_materialize_grads(False)     # else autograd fills a zero "gradient" for y_sums in every backward (40 launches)
         return y, y_sums
 
     @staticmethod
