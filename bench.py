@@ -258,7 +258,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=8, help='clips per GPU (BASELINE configs[1]: 8)')
     ap.add_argument('--cpu-batch', type=int, default=2, help='clips per CPU-baseline step (BASELINE.md §3: B = 2)')
-    ap.add_argument('--cpu-budget-s', type=float, default=400.0,
+    ap.add_argument('--cpu-budget-s', type=float, default=300.0,
                     help='--impl reference: drop to 1 clip per step if (steps+warmup) x first-step time exceeds this')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying the captured step')
