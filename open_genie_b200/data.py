@@ -224,6 +224,7 @@ class VideoBatchPrefetcher:
         self.loader, self.device, self.bgr, self.internal = loader, torch.device(device), bgr, internal
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned = [None, None]
+        self._inflight = [None, None]      # event after which a staging buffer's last H2D copy has completed
         self.h2d_bytes = 0
 
     def __len__(self):
@@ -232,6 +233,8 @@ class VideoBatchPrefetcher:
     def _stage(self, batch: Tensor, slot: int):
         if batch.dtype != torch.uint8:
             raise ValueError('VideoBatchPrefetcher needs uint8 frames: build the dataset with raw_uint8=True')
+        if self._inflight[slot] is not None:
+            self._inflight[slot].synchronize()      # the GPU may lag: do not overwrite a buffer whose copy is still in flight
         buf = self._pinned[slot]
         if buf is None or buf.shape != batch.shape:
             buf = torch.empty(batch.shape, dtype=torch.uint8).pin_memory()
@@ -240,6 +243,9 @@ class VideoBatchPrefetcher:
         self.h2d_bytes += buf.numel()
         with torch.cuda.stream(self.stream):
             dev = buf.to(self.device, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.stream)
+            self._inflight[slot] = copied
             video = frames_to_video(dev, self.bgr, self.internal)
             ev = torch.cuda.Event()
             ev.record(self.stream)

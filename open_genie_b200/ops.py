@@ -877,26 +877,28 @@ def _rows_bf16(x: Tensor) -> Tensor:
     return x
 
 
-_ROPE_TABLES = {}
-
-
 def _rope_table(freq: Tensor, npos: int) -> Optional[Tensor]:
-    """fp32 (npos, C/2, 2) table of (cos, sin)(pos * freq) for the fused RoPE+LayerNorm passes, cached per frequency
-    vector and sequence length (rebuilt if the `freq` parameter is replaced or modified). Never built while a CUDA
-    graph is being captured: a captured step uses the tables its warm-up steps created, or none."""
+    """fp32 (npos, C/2, 2) table of (cos, sin)(pos * freq) for the fused RoPE+LayerNorm passes. Cached ON the frequency
+    tensor object (per sequence length; rebuilt if the tensor is modified in place), so it lives and dies with the module's
+    `freq` parameter. Never built while a CUDA graph is being captured: a captured step uses the tables its warm-up steps
+    created, or none (the passes then evaluate sincosf per element — same values)."""
     if _os.environ.get('OG_ROPE_TABLE', '1') == '0':
         return None
-    key = (freq.data_ptr(), freq._version, int(npos), freq.device)
-    t = _ROPE_TABLES.get(key)
+    cache = getattr(freq, '_og_rope_tables', None)
+    if cache is None or cache[0] != (freq.data_ptr(), freq._version):
+        cache = ((freq.data_ptr(), freq._version), {})
+        try:
+            freq._og_rope_tables = cache
+        except Exception:
+            return None
+    t = cache[1].get(int(npos))
     if t is None:
         if torch.cuda.is_current_stream_capturing():
             return None
         C = 2 * freq.numel()
         t = torch.empty((npos, C // 2, 2), dtype=f32, device=freq.device)
         _lib.call('og_rope_table', freq.detach().float().contiguous().data_ptr(), int(npos), C, t.data_ptr(), _stream())
-        if len(_ROPE_TABLES) > 64:
-            _ROPE_TABLES.clear()
-        _ROPE_TABLES[key] = t
+        cache[1][int(npos)] = t
     return t
 
 
