@@ -67,11 +67,14 @@ uint64_t og_launch_count(void);
  * gn_sums (optional): fp64 [N][2] += (sum, sum of squares) of the bf16 output per sample — the og_gn_stats
  * result for a following GroupNorm(1, C) — produced in the GEMM epilogue when the tiling allows it, otherwise
  * by an internal og_gn_stats pass; either way the caller just zeroes it first. */
-/* workspace protocol (og_conv3d_fwd / og_conv3d_dgrad): the last 256 bytes of a workspace prepared with og_workspace_init
- * hold a self-resetting tile counter. With OG_IGEMM_DYNAMIC=1 in the environment the persistent GEMM CTAs draw their tiles
- * from it dynamically, so a launch that shares the GPU with another kernel does not wait for CTAs that could not become
- * resident (an experiment of round 2: no measurable gain, hence opt-in). Otherwise, or with an unprepared / NULL
- * workspace, tiles are assigned round-robin; results are identical. */
+/* workspace protocol (og_conv3d_fwd / og_conv3d_dgrad). A workspace PREPARED with og_workspace_init (call it once after
+ * allocating the buffer; it zeroes the buffer and reserves its last 4096 bytes for self-resetting counters) enables
+ *   - the in-kernel split-K finish: the last of a tile's split items to arrive reads the tile's partial sums back, adds the
+ *     bias, rounds, stores, emits the GroupNorm sums and re-zeroes its part of the workspace — no memset, no finish launch,
+ *     no statistics pass (OG_SPLITK_FUSED=0 disables it);
+ *   - with OG_IGEMM_DYNAMIC=1, dynamic tile scheduling for the persistent CTAs (an experiment: no measurable gain).
+ * An unprepared workspace gets the classic memset + partial sums + finish launch; NULL disables split-K. Results are
+ * identical up to the order of fp32 additions. Do not write to a prepared workspace from outside these calls. */
 int og_workspace_init(void* workspace, size_t workspace_bytes, og_stream_t stream);
 
 int og_conv3d_fwd(const void* x0, int c0, int kt, int kh, int kw, int pt, int ph, int pw, const void* x1, int c1,

@@ -21,6 +21,9 @@
 //   warps 2-5 epilogue: TMEM -> registers -> (+bias) -> global, double-buffered against the next tile's MMAs
 #include <stdlib.h>
 
+#include <utility>
+#include <vector>
+
 #include "og_host.cuh"
 #include "og_ptx.cuh"
 
@@ -75,7 +78,9 @@ struct IgemmParams {
   int swap;        // operand swap (see below): D^T[cout][256 voxels] = W . X^T, used when Cout tiles are 128 wide
   unsigned int* sched;  // dynamic tile scheduler state {magic, next item, CTAs done} in the caller's workspace, or NULL
   int splits;      // split-K factor (1 = none): each work item covers a k-block range and reduces into `ws`
-  float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zeroed by the launcher) when splits > 1
+  float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zero on entry) when splits > 1
+  unsigned int* tile_ctr;  // per-tile arrival counters (prepared workspace): the LAST split item of a tile finishes it in-kernel
+                           // (bias, cast, store, GroupNorm sums) and re-zeroes its part of `ws` — no memset, no finish launch
 };
 
 static constexpr int kBlockM = 128;
@@ -137,6 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   float* coef_s = reinterpret_cast<float*>(stage_s + 4 * 4096);          // [2][256] A, B of the current sample / N tile
   float* red_s = coef_s + 512;                                            // [256][2] column sums of the current tile
   double* stat_s = reinterpret_cast<double*>(red_s + 512);                // [2]
+  int* flag_s = reinterpret_cast<int*>(stat_s + 2);                       // [1] "this CTA finishes the tile" (fused split-K)
 
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -685,6 +691,105 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (p.splits > 1 && p.tile_ctr) {
+        // ---- fused split-K finish: the last of the `splits` items of this tile to arrive reduces nothing more — all
+        // partial sums are already in `ws` (L2 reductions) — it reads the tile back, adds the bias, rounds, stores, emits
+        // the GroupNorm sums and zeroes the tile for the next launch. Replaces a memset, a finish launch and a stats pass.
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et0 = threadIdx.x - 64;
+        if (et0 == 0) {
+          const unsigned int old = atomicAdd(p.tile_ctr + tile, 1u);
+          const int last = old == (unsigned int)(p.splits - 1);
+          if (last) p.tile_ctr[tile] = 0u;
+          flag_s[0] = last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (flag_s[0]) {
+          __threadfence();
+          float fs = 0.f, fss = 0.f;
+          int n_of_tile = 0;
+          for (int ms = 0; ms < p.m_sub; ++ms) {
+            const TileCoord tc = decode_m_tile(p, m_super * p.m_sub + ms);
+            n_of_tile = tc.n0;
+            const int dw = row & ((1 << p.bw_log2) - 1);
+            const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
+            const int dt = (row >> (p.bw_log2 + p.bh_log2)) & ((1 << p.bt_log2) - 1);
+            const int dn = row >> (p.bw_log2 + p.bh_log2 + p.bt_log2);
+            const int vn = tc.n0 + dn, vt = tc.t0 + dt, vh = tc.h0 + dh, vw = tc.w0 + dw;
+            if (!(vn < p.N && vt < p.T && vh < p.H && vw < p.W)) continue;
+            const long long vox = (((long long)vn * p.OT + vt) * p.OH + vh) * p.OW + vw;
+            const int col0 = n_tile * p.block_n;
+            for (int c = 0; c < p.block_n; c += 8) {
+              const int col = col0 + c;
+              if (col >= p.n_out) break;
+              float* wp = p.ws + vox * p.ldo + col;
+              float f[8];
+              if (p.vec_ok && col + 8 <= p.n_out) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(wp)), b = __ldcg(reinterpret_cast<const float4*>(wp) + 1);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                __stcg(reinterpret_cast<float4*>(wp), make_float4(0.f, 0.f, 0.f, 0.f));
+                __stcg(reinterpret_cast<float4*>(wp) + 1, make_float4(0.f, 0.f, 0.f, 0.f));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f[j] = (col + j < p.n_out) ? __ldcg(wp + j) : 0.f;
+                  if (col + j < p.n_out) __stcg(wp + j, 0.f);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (col + j < p.n_out) {
+                  if (p.bias0) f[j] += __ldg(p.bias0 + col + j);
+                  if (p.bias1) f[j] += __ldg(p.bias1 + col + j);
+                }
+              }
+              if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + vox * p.ldo + col;
+                if (p.vec_ok && col + 8 <= p.n_out) {
+                  *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                  *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                } else {
+                  for (int j = 0; j < 8; ++j)
+                    if (col + j < p.n_out) o[j] = f[j];
+                }
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.ldo + col;
+                if (p.gn_sums) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (col + j < p.n_out) {
+                      const float r = __bfloat162float(__float2bfloat16_rn(f[j]));
+                      fs += r;
+                      fss = fmaf(r, r, fss);
+                    }
+                }
+                if (p.vec_ok && col + 8 <= p.n_out) {
+                  uint4 u;
+                  u.x = pack_bf16x2(f[0], f[1]);
+                  u.y = pack_bf16x2(f[2], f[3]);
+                  u.z = pack_bf16x2(f[4], f[5]);
+                  u.w = pack_bf16x2(f[6], f[7]);
+                  *reinterpret_cast<uint4*>(o) = u;
+                } else {
+                  for (int j = 0; j < 8; ++j)
+                    if (col + j < p.n_out) o[j] = __float2bfloat16_rn(f[j]);
+                }
+              }
+            }
+          }
+          if (p.gn_sums) {
+            for (int o = 16; o > 0; o >>= 1) {
+              fs += __shfl_xor_sync(0xffffffffu, fs, o);
+              fss += __shfl_xor_sync(0xffffffffu, fss, o);
+            }
+            if (lane == 0) {
+              atomicAdd(&p.gn_sums[(long long)n_of_tile * 2], (double)fs);
+              atomicAdd(&p.gn_sums[(long long)n_of_tile * 2 + 1], (double)fss);
+            }
+          }
+        }
+      }
       if (p.fast_store && p.splits == 1 && (p.gn_sums || p.red_S)) {
         // flush this tile's fused reductions (all rows of a CTA tile belong to one sample: host-checked)
         const TileCoord tcf = decode_m_tile(p, m_super * p.m_sub);
@@ -790,6 +895,17 @@ struct IgemmLaunch {
   float* red_S = nullptr;
 };
 
+// workspaces prepared by og_workspace_init (all zero, magic in the tail): only those may use the in-kernel split-K finish
+static std::mutex g_ws_mutex;
+static std::vector<std::pair<const void*, size_t>> g_ws_prepared;
+static bool ws_prepared(const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (const auto& e : g_ws_prepared)
+    if (e.first == p && e.second == bytes) return true;
+  return false;
+}
+static constexpr size_t kWsTail = 4096;   // [0,256): scheduler state; [256,4096): per-tile arrival counters
+
 static IgemmSeg make_seg(int cin_blocks, int kt, int kh, int kw, int pt, int ph, int pw, int sgn) {
   IgemmSeg g;
   g.cin_blocks = cin_blocks;
@@ -868,9 +984,16 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   // dynamic tile scheduling: state lives in the last 256 bytes of the caller's workspace (og_workspace_init)
   p.sched = nullptr;
   size_t ws_usable = L.workspace_bytes;
-  if (L.workspace && L.workspace_bytes >= 4096) {
-    const size_t off = (L.workspace_bytes - 256) & ~(size_t)255;
+  unsigned int* tile_ctr = nullptr;
+  if (L.workspace && L.workspace_bytes >= 2 * kWsTail) {
+    const size_t off = (L.workspace_bytes - kWsTail) & ~(size_t)255;
     ws_usable = off;
+    static const bool fused_finish_on = [] {
+      const char* e = getenv("OG_SPLITK_FUSED");
+      return !(e && atoi(e) == 0);
+    }();
+    if (fused_finish_on && ws_prepared(L.workspace, L.workspace_bytes))
+      tile_ctr = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(L.workspace) + off + 256);
     // OFF by default: measured on 2 x B200 (profiles/r02k_*), the graphed data-parallel step takes 68.7 ms with either
     // assignment and the single-GPU step is within noise (64.9 dynamic vs 64.6 static) — the cost of overlapping the
     // all-reduce turned out to be power, not SM residency. OG_IGEMM_DYNAMIC=1 enables it.
@@ -893,7 +1016,10 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
       if (sp >= 2) {
         p.splits = sp;
         p.ws = reinterpret_cast<float*>(L.workspace);
-        OG_CHECK_CUDA(cudaMemsetAsync(L.workspace, 0, need, stream));
+        if (tile_ctr && tiles <= (long long)((kWsTail - 256) / sizeof(unsigned int)))
+          p.tile_ctr = tile_ctr;     // prepared workspace: `ws` is zero on entry and is left zero (fused finish)
+        else
+          OG_CHECK_CUDA(cudaMemsetAsync(L.workspace, 0, need, stream));
       }
     }
   }
@@ -961,7 +1087,8 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   // fused epilogue reductions need: staged bf16 stores, no split-K, every CTA tile inside one sample
   const int tiles_per_sample = p.tiles_w * p.tiles_h * p.tiles_t;
   const bool can_fuse = plain && p.fast_store && p.splits == 1 && bn == 1 && (tiles_per_sample % p.m_sub == 0) && n_out <= 65536;
-  p.gn_sums = (L.gn_sums && can_fuse) ? L.gn_sums : nullptr;
+  const bool can_fuse_splitk = plain && p.splits > 1 && p.tile_ctr && bn == 1 && !L.out_f32 && (tiles_per_sample % p.m_sub == 0);
+  p.gn_sums = (L.gn_sums && (can_fuse || can_fuse_splitk)) ? L.gn_sums : nullptr;
   p.red_S = (L.red_S && can_fuse) ? L.red_S : nullptr;
   p.red_x = reinterpret_cast<const __nv_bfloat16*>(L.red_x);
   p.red_A = L.red_A;
@@ -973,7 +1100,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   og_conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapB, p);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
-  if (p.splits > 1) {
+  if (p.splits > 1 && !p.tile_ctr) {
     const long long total = (long long)N * T * H * W * n_out;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
@@ -1053,12 +1180,22 @@ extern "C" int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void*
 // A workspace that was not initialised (no magic) simply gets the static tile assignment.
 extern "C" int og_workspace_init(void* workspace, size_t workspace_bytes, og_stream_t stream) {
   using namespace og;
-  OG_REQUIRE(workspace && workspace_bytes >= 4096, "workspace_init: need a workspace of at least 4096 bytes");
-  const size_t off = (workspace_bytes - 256) & ~(size_t)255;
+  OG_REQUIRE(workspace && workspace_bytes >= 2 * kWsTail, "workspace_init: need a workspace of at least %zu bytes", 2 * kWsTail);
+  const size_t off = (workspace_bytes - kWsTail) & ~(size_t)255;
   char* tail = reinterpret_cast<char*>(workspace) + off;
-  OG_CHECK_CUDA(cudaMemsetAsync(tail, 0, 256, (cudaStream_t)stream));
+  OG_CHECK_CUDA(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));   // partial sums + counters: all zero
   static const unsigned int magic = kSchedMagic;
   OG_CHECK_CUDA(cudaMemcpyAsync(tail, &magic, sizeof(magic), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    bool found = false;
+    for (auto& e : g_ws_prepared)
+      if (e.first == workspace) {
+        e.second = workspace_bytes;
+        found = true;
+      }
+    if (!found) g_ws_prepared.emplace_back(workspace, workspace_bytes);
+  }
   return OG_OK;
 }
 

@@ -144,7 +144,7 @@ class StepScope:
         if t is None or t.numel() < nbytes:
             if self.frozen or (dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()):
                 raise RuntimeError('open_genie_b200: split-K workspace of a captured training step would have to grow')
-            t = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+            t = torch.empty(nbytes + 8192, dtype=torch.uint8, device=dev)
             if dev.type == 'cuda':      # dynamic tile scheduler state in the buffer's tail (include/opengenie_b200.h)
                 _lib.call('og_workspace_init', t.data_ptr(), t.numel(), torch.cuda.current_stream(dev).cuda_stream)
             self.ws[dev] = t
