@@ -69,9 +69,9 @@ uint64_t og_launch_count(void);
  * by an internal og_gn_stats pass; either way the caller just zeroes it first. */
 /* workspace protocol (og_conv3d_fwd / og_conv3d_dgrad). A workspace PREPARED with og_workspace_init (call it once after
  * allocating the buffer; it zeroes the buffer and reserves its last 4096 bytes for self-resetting counters) enables
- *   - the in-kernel split-K finish: the last of a tile's split items to arrive reads the tile's partial sums back, adds the
- *     bias, rounds, stores, emits the GroupNorm sums and re-zeroes its part of the workspace — no memset, no finish launch,
- *     no statistics pass (OG_SPLITK_FUSED=0 disables it);
+ *   - with OG_SPLITK_FUSED=1, the in-kernel split-K finish: the last of a tile's split items to arrive reads the tile's
+ *     partial sums back, adds the bias, rounds, stores, emits the GroupNorm sums and re-zeroes its part of the workspace —
+ *     no memset, no finish launch, no statistics pass (an experiment: 98 fewer launches per step but 1-1.7 ms slower);
  *   - with OG_IGEMM_DYNAMIC=1, dynamic tile scheduling for the persistent CTAs (an experiment: no measurable gain).
  * An unprepared workspace gets the classic memset + partial sums + finish launch; NULL disables split-K. Results are
  * identical up to the order of fp32 additions. Do not write to a prepared workspace from outside these calls. */

@@ -709,71 +709,78 @@ __global__ void __launch_bounds__(kThreads, 1)
           __threadfence();
           float fs = 0.f, fss = 0.f;
           int n_of_tile = 0;
+          // a warp walks its 32 rows one at a time, its lanes spread over the row's columns (8 per lane): every access is a
+          // coalesced 1 KB row segment (the first version gave each thread a whole row: 32 scattered 32-byte pieces per
+          // warp instruction made the finishing CTA 50 us slower than the separate finish launch it replaced)
           for (int ms = 0; ms < p.m_sub; ++ms) {
             const TileCoord tc = decode_m_tile(p, m_super * p.m_sub + ms);
             n_of_tile = tc.n0;
-            const int dw = row & ((1 << p.bw_log2) - 1);
-            const int dh = (row >> p.bw_log2) & ((1 << p.bh_log2) - 1);
-            const int dt = (row >> (p.bw_log2 + p.bh_log2)) & ((1 << p.bt_log2) - 1);
-            const int dn = row >> (p.bw_log2 + p.bh_log2 + p.bt_log2);
-            const int vn = tc.n0 + dn, vt = tc.t0 + dt, vh = tc.h0 + dh, vw = tc.w0 + dw;
-            if (!(vn < p.N && vt < p.T && vh < p.H && vw < p.W)) continue;
-            const long long vox = (((long long)vn * p.OT + vt) * p.OH + vh) * p.OW + vw;
             const int col0 = n_tile * p.block_n;
-            for (int c = 0; c < p.block_n; c += 8) {
-              const int col = col0 + c;
-              if (col >= p.n_out) break;
-              float* wp = p.ws + vox * p.ldo + col;
-              float f[8];
-              if (p.vec_ok && col + 8 <= p.n_out) {
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(wp)), b = __ldcg(reinterpret_cast<const float4*>(wp) + 1);
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-                __stcg(reinterpret_cast<float4*>(wp), make_float4(0.f, 0.f, 0.f, 0.f));
-                __stcg(reinterpret_cast<float4*>(wp) + 1, make_float4(0.f, 0.f, 0.f, 0.f));
-              } else {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r = q * 32 + rr;
+              const int dw = r & ((1 << p.bw_log2) - 1);
+              const int dh = (r >> p.bw_log2) & ((1 << p.bh_log2) - 1);
+              const int dt = (r >> (p.bw_log2 + p.bh_log2)) & ((1 << p.bt_log2) - 1);
+              const int dn = r >> (p.bw_log2 + p.bh_log2 + p.bt_log2);
+              const int vn = tc.n0 + dn, vt = tc.t0 + dt, vh = tc.h0 + dh, vw = tc.w0 + dw;
+              if (!(vn < p.N && vt < p.T && vh < p.H && vw < p.W)) continue;
+              const long long vox = (((long long)vn * p.OT + vt) * p.OH + vh) * p.OW + vw;
+              for (int c = lane * 8; c < p.block_n; c += 256) {
+                const int col = col0 + c;
+                if (col >= p.n_out) break;
+                float* wp = p.ws + vox * p.ldo + col;
+                float f[8];
+                if (p.vec_ok && col + 8 <= p.n_out) {
+                  const float4 a = __ldcg(reinterpret_cast<const float4*>(wp)), b = __ldcg(reinterpret_cast<const float4*>(wp) + 1);
+                  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                  __stcg(reinterpret_cast<float4*>(wp), make_float4(0.f, 0.f, 0.f, 0.f));
+                  __stcg(reinterpret_cast<float4*>(wp) + 1, make_float4(0.f, 0.f, 0.f, 0.f));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    f[j] = (col + j < p.n_out) ? __ldcg(wp + j) : 0.f;
+                    if (col + j < p.n_out) __stcg(wp + j, 0.f);
+                  }
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  f[j] = (col + j < p.n_out) ? __ldcg(wp + j) : 0.f;
-                  if (col + j < p.n_out) __stcg(wp + j, 0.f);
+                  if (col + j < p.n_out) {
+                    if (p.bias0) f[j] += __ldg(p.bias0 + col + j);
+                    if (p.bias1) f[j] += __ldg(p.bias1 + col + j);
+                  }
                 }
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (col + j < p.n_out) {
-                  if (p.bias0) f[j] += __ldg(p.bias0 + col + j);
-                  if (p.bias1) f[j] += __ldg(p.bias1 + col + j);
-                }
-              }
-              if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + vox * p.ldo + col;
-                if (p.vec_ok && col + 8 <= p.n_out) {
-                  *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                  *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                if (p.out_f32) {
+                  float* o = reinterpret_cast<float*>(p.out) + vox * p.ldo + col;
+                  if (p.vec_ok && col + 8 <= p.n_out) {
+                    *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                  } else {
+                    for (int j = 0; j < 8; ++j)
+                      if (col + j < p.n_out) o[j] = f[j];
+                  }
                 } else {
-                  for (int j = 0; j < 8; ++j)
-                    if (col + j < p.n_out) o[j] = f[j];
-                }
-              } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.ldo + col;
-                if (p.gn_sums) {
+                  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * p.ldo + col;
+                  if (p.gn_sums) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (col + j < p.n_out) {
-                      const float r = __bfloat162float(__float2bfloat16_rn(f[j]));
-                      fs += r;
-                      fss = fmaf(r, r, fss);
-                    }
-                }
-                if (p.vec_ok && col + 8 <= p.n_out) {
-                  uint4 u;
-                  u.x = pack_bf16x2(f[0], f[1]);
-                  u.y = pack_bf16x2(f[2], f[3]);
-                  u.z = pack_bf16x2(f[4], f[5]);
-                  u.w = pack_bf16x2(f[6], f[7]);
-                  *reinterpret_cast<uint4*>(o) = u;
-                } else {
-                  for (int j = 0; j < 8; ++j)
-                    if (col + j < p.n_out) o[j] = __float2bfloat16_rn(f[j]);
+                    for (int j = 0; j < 8; ++j)
+                      if (col + j < p.n_out) {
+                        const float rv = __bfloat162float(__float2bfloat16_rn(f[j]));
+                        fs += rv;
+                        fss = fmaf(rv, rv, fss);
+                      }
+                  }
+                  if (p.vec_ok && col + 8 <= p.n_out) {
+                    uint4 u;
+                    u.x = pack_bf16x2(f[0], f[1]);
+                    u.y = pack_bf16x2(f[2], f[3]);
+                    u.z = pack_bf16x2(f[4], f[5]);
+                    u.w = pack_bf16x2(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(o) = u;
+                  } else {
+                    for (int j = 0; j < 8; ++j)
+                      if (col + j < p.n_out) o[j] = __float2bfloat16_rn(f[j]);
+                  }
                 }
               }
             }
@@ -988,9 +995,13 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (L.workspace && L.workspace_bytes >= 2 * kWsTail) {
     const size_t off = (L.workspace_bytes - kWsTail) & ~(size_t)255;
     ws_usable = off;
+    // in-kernel split-K finish: OFF by default. Measured on one B200 (profiles/r02p_*): it removes 98 launches per step
+    // (memset + finish + statistics pass) yet the graphed step is 64.0-64.7 ms with it and 62.95 ms without — the last
+    // arriver's fence + read-back sits on the tail of every split launch, while the three small launches it replaces cost
+    // ~3 us each inside a graph. OG_SPLITK_FUSED=1 enables it.
     static const bool fused_finish_on = [] {
       const char* e = getenv("OG_SPLITK_FUSED");
-      return !(e && atoi(e) == 0);
+      return e && atoi(e) == 1;
     }();
     if (fused_finish_on && ws_prepared(L.workspace, L.workspace_bytes))
       tile_ctr = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(L.workspace) + off + 256);

@@ -1,8 +1,8 @@
 #!/bin/bash
-# quick single-GPU check: full GPU suite + bench (graph) with and without a switch given as $2 (e.g. OG_SPLITK_FUSED=0)
+# quick single-GPU check: full GPU suite + bench (graph) with and without a switch given as $2 (e.g. OG_SPLITK_FUSED=1)
 set -u
 TAG=${1:-r02o}
-ALT=${2:-OG_SPLITK_FUSED=0}
+ALT=${2:-OG_SPLITK_FUSED=1}
 O=gpurun_out
 python -m pytest tests -m gpu -q > $O/${TAG}_gputest.log 2>&1; tail -4 $O/${TAG}_gputest.log
 show() { python -c "import json,sys;d=json.loads(open('$1').read().strip().splitlines()[-1]);k=d['roofline']['kernels'];print('$2',round(d['value'],1),round(d['ms_per_step'],2),d['clocks']['sm_mhz'],'launches/step',d['gpu_launches']//d['steps'],'igemm',round(k['og_conv_igemm_kernel']['ms_per_step'],2),'wgrad',round(k['og_conv_wgrad_kernel']['ms_per_step'],2))" || tail -3 ${1%.json}.err; }
