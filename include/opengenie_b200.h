@@ -63,7 +63,9 @@ uint64_t og_launch_count(void);
  * SpaceTimeAttention, attention.py:472).
  * Reads outside [0,T)x[0,H)x[0,W) are zero (pad_mode='constant').
  * workspace (optional, may be NULL): N*T*H*W*cout fp32 of scratch enables split-K for problems whose tiles
- * cannot fill the 148 SMs (small T*H*W, deep K); without it the same result is computed unsplit.
+ * cannot fill the 148 SMs (small T*H*W, deep K); without it the same result is computed unsplit. With room for one
+ * such slab per split (20 MB always suffices) every split stores its partial tile with plain stores and the finish pass
+ * adds the slabs (and emits gn_sums); a smaller workspace is zeroed and reduced into with red.global.add.
  * gn_sums (optional): fp64 [N][2] += (sum, sum of squares) of the bf16 output per sample — the og_gn_stats
  * result for a following GroupNorm(1, C) — produced in the GEMM epilogue when the tiling allows it, otherwise
  * by an internal og_gn_stats pass; either way the caller just zeroes it first. */

@@ -79,6 +79,9 @@ struct IgemmParams {
   unsigned int* sched;  // dynamic tile scheduler state {magic, next item, CTAs done} in the caller's workspace, or NULL
   int splits;      // split-K factor (1 = none): each work item covers a k-block range and reduces into `ws`
   float* ws;       // fp32 [voxels][n_out] partial-sum workspace (zero on entry) when splits > 1
+  long long ws_slab;  // > 0: every split item STORES its partial tile into its own slab ws[split*ws_slab + ...] (no atomics,
+                      // no memset; the finish pass adds the slabs); 0: red.global.add into one zeroed slab
+  int dbg;         // timing experiments only (OG_IGEMM_DBG): 1 = skip the split-K epilogue's global writes
   unsigned int* tile_ctr;  // per-tile arrival counters (prepared workspace): the LAST split item of a tile finishes it in-kernel
                            // (bias, cast, store, GroupNorm sums) and re-zeroes its part of `ws` — no memset, no finish launch
 };
@@ -463,18 +466,33 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint32_t v[32];
           tmem_ld_32x32(t_addr + c, v);
           tmem_ld_wait();
-          if (row_ok) {
-            float* dst = p.ws + vox * p.ldo + col0 + c;
-            if (p.vec_ok && col0 + c + 32 <= p.n_out) {
+          if (row_ok && p.dbg != 1) {
+            if (p.ws_slab) {
+              // own slab: plain stores (each thread fills one 128-byte line of its row per chunk)
+              float* dst = p.ws + (long long)(item - tile * p.splits) * p.ws_slab + vox * p.ldo + col0 + c;
+              if (p.vec_ok && col0 + c + 32 <= p.n_out) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
-                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
-                             "f"(__uint_as_float(v[j + 3]))
-                             : "memory");
+                for (int j = 0; j < 32; j += 4)
+                  __stcg(reinterpret_cast<float4*>(dst + j),
+                         make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3])));
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + c + j < p.n_out) dst[j] = __uint_as_float(v[j]);
+              }
             } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + c + j < p.n_out) atomicAdd(dst + j, __uint_as_float(v[j]));
+              float* dst = p.ws + vox * p.ldo + col0 + c;
+              if (p.vec_ok && col0 + c + 32 <= p.n_out) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                               "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                               "f"(__uint_as_float(v[j + 3]))
+                               : "memory");
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + c + j < p.n_out) atomicAdd(dst + j, __uint_as_float(v[j]));
+              }
             }
           }
         }
@@ -842,19 +860,76 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // split-K finish: out = cast(ws + bias0 + bias1)
-__global__ void og_splitk_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias0,
-                                        const float* __restrict__ bias1, void* __restrict__ out, int out_f32,
-                                        int n_out, long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+// Finish pass of a split-K launch: out = cast(sum of the `nslab` partial slabs + bias), and — optionally — the per-sample
+// GroupNorm(1, C) sums of the bf16-rounded result (what og_gn_stats would compute in another pass over `out`).
+// grid = (chunks, samples); `per_sample` = T*H*W*n_out elements.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    og_splitk_finish_kernel(const float* __restrict__ ws, long long slab, int nslab, const float* __restrict__ bias0,
+                            const float* __restrict__ bias1, void* __restrict__ out, int out_f32, int n_out,
+                            long long per_sample, double* __restrict__ gn_sums) {
+  const long long base = (long long)blockIdx.y * per_sample;
+  float s = 0.f, ss = 0.f;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x * VEC) {
+    float v[VEC];
+    if (VEC == 4) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(ws + base + i));
+      v[0] = a.x; v[1 % VEC] = a.y; v[2 % VEC] = a.z; v[3 % VEC] = a.w;
+      for (int k = 1; k < nslab; ++k) {
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(ws + (long long)k * slab + base + i));
+        v[0] += b.x; v[1 % VEC] += b.y; v[2 % VEC] += b.z; v[3 % VEC] += b.w;
+      }
+    } else {
+      v[0] = __ldcg(ws + base + i);
+      for (int k = 1; k < nslab; ++k) v[0] += __ldcg(ws + (long long)k * slab + base + i);
+    }
     const int col = (int)(i % n_out);
-    float v = ws[i];
-    if (bias0) v += __ldg(bias0 + col);
-    if (bias1) v += __ldg(bias1 + col);
-    if (out_f32)
-      reinterpret_cast<float*>(out)[i] = v;
-    else
-      reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      if (bias0) v[e] += __ldg(bias0 + col + e);
+      if (bias1) v[e] += __ldg(bias1 + col + e);
+    }
+    if (out_f32) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) reinterpret_cast<float*>(out)[base + i + e] = v[e];
+    } else {
+      __nv_bfloat16 h[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        h[e] = __float2bfloat16_rn(v[e]);
+        const float r = __bfloat162float(h[e]);
+        s += r;
+        ss = fmaf(r, r, ss);
+      }
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + base + i;
+      if (VEC == 4)
+        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
+      else
+        o[0] = h[0];
+    }
+  }
+  if (gn_sums) {
+    __shared__ float red[2][8];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, off);
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = s;
+      red[1][threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        a += (double)red[0][w];
+        b += (double)red[1][w];
+      }
+      atomicAdd(gn_sums + 2 * blockIdx.y, a);
+      atomicAdd(gn_sums + 2 * blockIdx.y + 1, b);
+    }
   }
 }
 
@@ -1017,6 +1092,9 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   // split-K when the tiles cannot fill the machine and each has a long K loop
   p.splits = 1;
   p.ws = nullptr;
+  p.ws_slab = 0;
+  p.dbg = 0;
+  if (const char* e = getenv("OG_IGEMM_DBG")) p.dbg = atoi(e);
   if (plain) {
     const long long tiles = (long long)((p.num_m_tiles + p.m_sub - 1) / p.m_sub) * p.num_n_tiles;
     const size_t need = (size_t)N * T * H * W * n_out * sizeof(float);
@@ -1027,8 +1105,16 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
       if (sp >= 2) {
         p.splits = sp;
         p.ws = reinterpret_cast<float*>(L.workspace);
+        // one slab per split when the workspace holds them (plain stores, no memset); OG_SPLITK_SLABS=0: one zeroed slab
+        // that the items reduce into with red.global.add (the round-1 form, kept for small workspaces)
+        static const bool slabs_on = [] {
+          const char* e = getenv("OG_SPLITK_SLABS");
+          return !(e && atoi(e) == 0);
+        }();
         if (tile_ctr && tiles <= (long long)((kWsTail - 256) / sizeof(unsigned int)))
           p.tile_ctr = tile_ctr;     // prepared workspace: `ws` is zero on entry and is left zero (fused finish)
+        else if (slabs_on && ws_usable >= need * (size_t)sp)
+          p.ws_slab = (long long)(need / sizeof(float));
         else
           OG_CHECK_CUDA(cudaMemsetAsync(L.workspace, 0, need, stream));
       }
@@ -1111,16 +1197,29 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   og_conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(mapA0, mapA1, mapB, p);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
+  bool finish_did_stats = false;
   if (p.splits > 1 && !p.tile_ctr) {
-    const long long total = (long long)N * T * H * W * n_out;
-    long long blocks = (total + 255) / 256;
-    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    og_splitk_finish_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p.ws, L.bias0, L.bias1, L.out, L.out_f32, n_out, total);
+    const long long per_sample = (long long)T * H * W * n_out;
+    const int nslab = p.ws_slab ? p.splits : 1;
+    finish_did_stats = L.gn_sums && !L.out_f32;
+    double* gs = finish_did_stats ? L.gn_sums : nullptr;
+    const int vec = (n_out % 4 == 0) ? 4 : 1;
+    long long bx = (per_sample / vec + 255) / 256;
+    const long long cap = ((long long)num_sms() * 8 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)N);
+    if (vec == 4)
+      og_splitk_finish_kernel<4><<<grid, 256, 0, stream>>>(p.ws, p.ws_slab, nslab, L.bias0, L.bias1, L.out, L.out_f32,
+                                                            n_out, per_sample, gs);
+    else
+      og_splitk_finish_kernel<1><<<grid, 256, 0, stream>>>(p.ws, p.ws_slab, nslab, L.bias0, L.bias1, L.out, L.out_f32,
+                                                            n_out, per_sample, gs);
     OG_CHECK_CUDA(cudaGetLastError());
     g_launches.fetch_add(1);
   }
   // requested reductions that could not be fused: run the stand-alone passes on the stored output
-  if (L.gn_sums && !p.gn_sums) {
+  if (L.gn_sums && !p.gn_sums && !finish_did_stats) {
     OG_REQUIRE(!L.out_f32 && plain, "conv3d: GroupNorm statistics need a plain bf16 output");
     int r = og_gn_stats(L.out, N, (int64_t)T * H * W, n_out, 1, L.gn_sums, (og_stream_t)stream);
     if (r != OG_OK) return r;

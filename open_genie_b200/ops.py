@@ -139,7 +139,8 @@ class StepScope:
         self.frozen = False
 
     def workspace(self, dev, nbytes: int):
-        nbytes = min(max(nbytes, 1 << 20), 1 << 30)
+        # >= 24 MB: room for one partial-sum slab per split (splits x tiles <= 148 tiles of 128 x 256 fp32 = 19.4 MB)
+        nbytes = min(max(nbytes, 24 << 20), 1 << 30)
         t = self.ws.get(dev)
         if t is None or t.numel() < nbytes:
             if self.frozen or (dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()):
