@@ -223,11 +223,19 @@ __global__ void __launch_bounds__(kFaThreads, 2)
         tmem_ld_32x32(tS + lane_addr + c, v);
         tmem_ld_wait();
         float pf[32];
+        if (kv_valid >= kTile) {  // whole key tile (every tile but possibly the last): no per-element select / compare
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = ex2_approx(fmaf(__uint_as_float(v[i]), cl2, -mn));
-          pf[i] = (kv_valid >= kTile || c + i < kv_valid) ? e : 0.f;
-          ls += pf[i];
+          for (int i = 0; i < 32; ++i) {
+            pf[i] = ex2_approx(fmaf(__uint_as_float(v[i]), cl2, -mn));
+            ls += pf[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), cl2, -mn));
+            pf[i] = (c + i < kv_valid) ? e : 0.f;
+            ls += pf[i];
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -586,6 +594,341 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, software-pipelined (round 2). Same two passes and the same math as og_flash_attn_bwd_kernel above, but the
+// S accumulator is DOUBLE-buffered in TMEM (S0 | S1 | dP | acc = 128+128+128+128 columns) and the softmax is split in
+// two phases so that the tensor pipe never waits for a whole softmax and the softmax warps never wait for a whole
+// S/dP pair:
+//   phase A(it): P = 2^(S*c - lse) from S(it)              needs S(it)  — issued one iteration EARLY
+//   phase B(it): dS = P * (dP - delta) from dP(it)          needs dP(it) — issued when phase B(it-1) has read dP(it-1)
+// MMA issue order per iteration:  dP(it) | dV,dK / dQ of it-1 | S(it+1).
+// In the first version the order was S,dP(it) -> softmax(it) -> S,dP(it+1): the softmax warps idled while S/dP ran
+// (~700 clk of a ~3400 clk iteration) and the MMAs idled during the softmax.
+// MODE 1 has no P tile in shared memory and uses the room for a third K/V stage.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kFaBwdThreads, 1)
+    og_flash_attn_bwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                              const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
+                              const FaBwdParams p) {
+  constexpr int kStages = MODE == 0 ? 2 : 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sFix = smem;                    // stationary pair: MODE 0: K_j, V_j ; MODE 1: Q_i, dO_i   (2 x 16 KiB)
+  uint8_t* sStr = smem + 2 * kTileBytes;   // streamed pair, kStages x (2 x 16 KiB)   (MODE 1: runs into the P region)
+  uint8_t* sP = smem + 6 * kTileBytes;     // P  bf16 [2 buffers][2 k-blocks][128][128 B]   (MODE 0 only)
+  uint8_t* sDS = smem + 10 * kTileBytes;   // dS bf16, same shape
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * kTileBytes);
+  uint64_t* fix_full = bars;
+  uint64_t* str_full = bars + 1;   // [3]
+  uint64_t* str_empty = bars + 4;  // [3]
+  uint64_t* s_full = bars + 7;     // [2]
+  uint64_t* dp_full = bars + 9;
+  uint64_t* dp_free = bars + 10;
+  uint64_t* p_ready = bars + 11;
+  uint64_t* acc_ready = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  int id = blockIdx.x;
+  const int own = id % p.tiles;  // MODE 0: kv tile ; MODE 1: q tile
+  id /= p.tiles;
+  const int h = id % p.nh;
+  const int seq = id / p.nh;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    tma_prefetch_desc(&mapDO);
+    mbar_init(fix_full, 1);
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&str_full[s], 1);
+      mbar_init(&str_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(dp_full, 1);
+    mbar_init(dp_free, 8);
+    mbar_init(p_ready, 8);
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS0 = tmem_base, tDP = tmem_base + 256, tAcc0 = tmem_base + 384, tAcc1 = tmem_base + 448;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(fix_full, 2 * kTileBytes);
+      if (MODE == 0) {
+        tma_load_3d(sFix, &mapK, fix_full, h * kD, own * kTile, seq);
+        tma_load_3d(sFix + kTileBytes, &mapV, fix_full, h * kD, own * kTile, seq);
+      } else {
+        tma_load_3d(sFix, &mapQ, fix_full, h * kD, own * kTile, seq);
+        tma_load_3d(sFix + kTileBytes, &mapDO, fix_full, h * kD, own * kTile, seq);
+      }
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 1;   // the first pass over the ring finds every slot free
+    for (int it = 0; it < p.tiles; ++it) {
+      mbar_wait(&str_empty[st], ph);
+      if (elect_one()) {
+        mbar_expect_tx(&str_full[st], 2 * kTileBytes);
+        uint8_t* d = sStr + st * 2 * kTileBytes;
+        if (MODE == 0) {
+          tma_load_3d(d, &mapQ, &str_full[st], h * kD, it * kTile, seq);
+          tma_load_3d(d + kTileBytes, &mapDO, &str_full[st], h * kD, it * kTile, seq);
+        } else {
+          tma_load_3d(d, &mapK, &str_full[st], h * kD, it * kTile, seq);
+          tma_load_3d(d + kTileBytes, &mapV, &str_full[st], h * kD, it * kTile, seq);
+        }
+      }
+      __syncwarp();
+      if (++st == kStages) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0u, 0u);  // S, dP: both operands K-major
+    const uint32_t idesc_mm = umma_idesc_bf16(128, 64, 1u, 1u);   // dV, dK: A (P / dS transposed) and B MN-major
+    const uint32_t idesc_km = umma_idesc_bf16(128, 64, 0u, 1u);   // dQ: A = dS K-major, B = K MN-major
+    const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+    const uint32_t fixa = smem_u32(sFix), str0 = smem_u32(sStr);
+    mbar_wait(fix_full, 0);
+    // ring position of tile `it` (st_cur) and of tile it+1 (st_nxt); parities of their `full` barriers
+    int st_prev = 0, st_cur = 0, st_nxt = kStages > 1 ? 1 : 0;
+    uint32_t ph_nxt = 0;
+    {  // S(0)
+      mbar_wait(&str_full[0], 0);
+      tc_fence_after();
+      const uint32_t q_addr = MODE == 0 ? str0 : fixa, k_addr = MODE == 0 ? fixa : str0;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16_ss(tS0, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[0]);
+      }
+      __syncwarp();
+    }
+    for (int it = 0; it <= p.tiles; ++it) {
+      if (it < p.tiles) {  // dP(it): the slot of tile `it` is loaded (S(it) waited for it)
+        if (it > 0) {
+          mbar_wait(dp_free, (it - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t stra = str0 + st_cur * 2 * kTileBytes;
+        const uint32_t do_addr = (MODE == 0 ? stra : fixa) + kTileBytes, v_addr = (MODE == 0 ? fixa : stra) + kTileBytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k)
+            umma_bf16_ss(tDP, umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                         umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+          umma_commit(dp_full);
+        }
+        __syncwarp();
+      }
+      if (it > 0) {  // gradient MMAs of tile it-1 (P / dS buffer (it-1) & 1, stream slot st_prev)
+        const int jj = it - 1;
+        mbar_wait(p_ready, jj & 1);
+        tc_fence_after();
+        const uint32_t stra = str0 + st_prev * 2 * kTileBytes;
+        const uint32_t p_addr = p_base + (jj & 1) * 2 * kTileBytes, ds_addr = ds_base + (jj & 1) * 2 * kTileBytes;
+        if (!elect_one()) {
+        } else if (MODE == 0) {
+          const uint32_t q_addr = stra, do_addr = stra + kTileBytes;
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k) {  // K dim = 128 query rows, 16 per MMA
+            umma_bf16_ss(tAcc0, umma_smem_desc_sw128(p_addr + k * 2048, kTileBytes, 1024),
+                         umma_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_mm, (jj > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss(tAcc1, umma_smem_desc_sw128(ds_addr + k * 2048, kTileBytes, 1024),
+                         umma_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_mm, (jj > 0 || k > 0) ? 1u : 0u);
+          }
+        } else {
+          const uint32_t k_addr = stra;
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k)  // K dim = 128 keys
+            umma_bf16_ss(tAcc0, umma_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                         umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_km, (jj > 0 || k > 0) ? 1u : 0u);
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&str_empty[st_prev]);
+        __syncwarp();
+      }
+      if (it + 1 < p.tiles) {  // S(it+1) into the S buffer phase A(it-1) has finished with (implied by p_ready(it-1))
+        mbar_wait(&str_full[st_nxt], ph_nxt);
+        tc_fence_after();
+        const uint32_t stra = str0 + st_nxt * 2 * kTileBytes;
+        const uint32_t q_addr = MODE == 0 ? stra : fixa, k_addr = MODE == 0 ? fixa : stra;
+        const uint32_t tS = tS0 + (((it + 1) & 1) ? 128u : 0u);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k)
+            umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[(it + 1) & 1]);
+        }
+        __syncwarp();
+      }
+      st_prev = st_cur;
+      st_cur = st_nxt;
+      if (++st_nxt == kStages) {
+        st_nxt = 0;
+        ph_nxt ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit(acc_ready);
+    __syncwarp();
+  } else {
+    // 8 warps: warps w and w+4 share TMEM lane quarter (w & 3) and split the 128 columns of S / dP in halves.
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = qd * 32 + lane;  // TMEM lane: query row of the current pair
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float cl2 = p.scale * 1.4426950408889634f;
+    float lse_fix = 0.f, delta_fix = 0.f;
+    if (MODE == 1) {
+      const int qrow = own * kTile + row;
+      if (qrow < p.S) {
+        lse_fix = p.lse[((long long)seq * p.nh + h) * p.S + qrow] * 1.4426950408889634f;
+        delta_fix = p.delta[((long long)seq * p.nh + h) * p.S + qrow];
+      }
+    }
+    // MODE 0 streams the query tiles: the per-row lse / delta of tile it+1 are fetched while tile it is processed
+    // (as dependent loads at the top of the iteration they were 12 % of the softmax warps' time)
+    const float* lse_row = p.lse + ((long long)seq * p.nh + h) * p.S;
+    const float* delta_row = p.delta + ((long long)seq * p.nh + h) * p.S;
+    float lse_nxt = 0.f, delta_nxt = 0.f;
+    if (MODE == 0 && row < p.S) {
+      lse_nxt = __ldg(lse_row + row);
+      delta_nxt = __ldg(delta_row + row);
+    }
+    for (int it = 0; it < p.tiles; ++it) {
+      const int q_tile = MODE == 0 ? it : own, kv_tile = MODE == 0 ? own : it;
+      const int qrow = q_tile * kTile + row;
+      float lse2 = lse_fix, delta = delta_fix;
+      if (MODE == 0) {
+        lse2 = lse_nxt * 1.4426950408889634f;
+        delta = delta_nxt;
+        if (qrow + kTile < p.S) {
+          lse_nxt = __ldg(lse_row + qrow + kTile);
+          delta_nxt = __ldg(delta_row + qrow + kTile);
+        }
+      }
+      const bool q_ok = qrow < p.S;
+      const int kv_valid = p.S - kv_tile * kTile;
+      const bool full = (q_tile + 1) * kTile <= p.S && kv_valid >= kTile;  // warp-uniform fast path
+      const uint32_t tS = tS0 + ((it & 1) ? 128u : 0u);
+      float pf[64];
+      // ---- phase A: probabilities from S(it)
+      mbar_wait(&s_full[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        const int c = half * 64 + cc;
+        uint32_t vs[32];
+        tmem_ld_32x32(tS + lane_addr + c, vs);
+        tmem_ld_wait();
+        if (full) {  // whole tiles: no per-element select / compare (they were a quarter of the issued instructions)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pf[cc + i] = ex2_approx(fmaf(__uint_as_float(vs[i]), cl2, -lse2));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float pv = ex2_approx(fmaf(__uint_as_float(vs[i]), cl2, -lse2));
+            pf[cc + i] = (q_ok && (c + i < kv_valid)) ? pv : 0.f;
+          }
+        }
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const int col = c + i;
+            uint4 u;
+            u.x = pack_bf16x2(pf[cc + i], pf[cc + i + 1]);
+            u.y = pack_bf16x2(pf[cc + i + 2], pf[cc + i + 3]);
+            u.z = pack_bf16x2(pf[cc + i + 4], pf[cc + i + 5]);
+            u.w = pack_bf16x2(pf[cc + i + 6], pf[cc + i + 7]);
+            st_swizzled_chunk(sP + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
+          }
+        }
+      }
+      // ---- phase B: dS from dP(it); the dP accumulator is handed back as soon as it sits in registers
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+      uint32_t vd0[32], vd1[32];
+      tmem_ld_32x32(tDP + lane_addr + half * 64, vd0);
+      tmem_ld_32x32(tDP + lane_addr + half * 64 + 32, vd1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dp_free);
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        const int c = half * 64 + cc;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const int col = c + i;
+          float df[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            df[e] = pf[cc + i + e] * (__uint_as_float(cc == 0 ? vd0[i + e] : vd1[i + e]) - delta);
+          uint4 u;
+          u.x = pack_bf16x2(df[0], df[1]);
+          u.y = pack_bf16x2(df[2], df[3]);
+          u.z = pack_bf16x2(df[4], df[5]);
+          u.w = pack_bf16x2(df[6], df[7]);
+          st_swizzled_chunk(sDS + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    // accumulators complete: TMEM lane = output row (kv row in MODE 0, query row in MODE 1); the two warps of a
+    // lane quarter take 32 of the 64 columns each. dK / dQ carry the softmax scale here.
+    mbar_wait_relaxed(acc_ready, 0);
+    tc_fence_after();
+    const int orow = own * kTile + row;
+    for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
+      __nv_bfloat16* base = MODE == 1 ? p.dq : (a == 0 ? p.dv : p.dk);
+      const uint32_t tacc = a == 0 ? tAcc0 : tAcc1;
+      const float osc = (MODE == 0 && a == 0) ? 1.f : p.scale;
+      const int c = half * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(tacc + lane_addr + c, v);
+      tmem_ld_wait();
+      if (orow < p.S) {
+        __nv_bfloat16* dst = base + ((long long)seq * p.S + orow) * p.C + h * kD + c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[i]) * osc, __uint_as_float(v[i + 1]) * osc);
+          u.y = pack_bf16x2(__uint_as_float(v[i + 2]) * osc, __uint_as_float(v[i + 3]) * osc);
+          u.z = pack_bf16x2(__uint_as_float(v[i + 4]) * osc, __uint_as_float(v[i + 5]) * osc);
+          u.w = pack_bf16x2(__uint_as_float(v[i + 6]) * osc, __uint_as_float(v[i + 7]) * osc);
+          *reinterpret_cast<uint4*>(dst + i) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // delta[seq][h][s] = sum_d dO * O   (one warp per row, lanes over the head's 64 dims)
 __global__ void og_attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                      float* __restrict__ delta, long long rows, int S, int C, int nh) {
@@ -687,13 +1030,29 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
                                        (int)smem_bytes));
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
+    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_bytes));
     attr = true;
   }
   const long long grid = (long long)nseq * n_head * p.tiles;
-  og_flash_attn_bwd_kernel<0><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
-  OG_CHECK_CUDA(cudaGetLastError());
-  og_flash_attn_bwd_kernel<1><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
-  OG_CHECK_CUDA(cudaGetLastError());
+  // OG_FLASH_BWD_V1=1: the un-pipelined first version (kept for A/B timing)
+  static const bool v1 = [] {
+    const char* e = getenv("OG_FLASH_BWD_V1");
+    return e && atoi(e) == 1;
+  }();
+  if (v1) {
+    og_flash_attn_bwd_kernel<0><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+    OG_CHECK_CUDA(cudaGetLastError());
+    og_flash_attn_bwd_kernel<1><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+    OG_CHECK_CUDA(cudaGetLastError());
+  } else {
+    og_flash_attn_bwd2_kernel<0><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+    OG_CHECK_CUDA(cudaGetLastError());
+    og_flash_attn_bwd2_kernel<1><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+    OG_CHECK_CUDA(cudaGetLastError());
+  }
   g_launches.fetch_add(2);
   return OG_OK;
 }

@@ -22,3 +22,14 @@ _lib.call('og_flash_attn_bwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), out.dat
 e2.record(); torch.cuda.synchronize()
 fl = 4.0 * S * S * 64 * nseq * nh
 print(f'fwd {e0.elapsed_time(e1):.3f} ms {fl / e0.elapsed_time(e1) * 1e-9:.0f} TFLOP/s ; bwd {e1.elapsed_time(e2):.3f} ms {2.5 * fl / e1.elapsed_time(e2) * 1e-9:.0f} TFLOP/s')
+# steady-state timing (5 launches each) and checksums for A/B runs (OG_FLASH_BWD_V1=1 selects the first backward version)
+e0.record()
+for _ in range(5):
+    _lib.call('og_flash_attn_fwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), None, None, lse.data_ptr(), nseq, S, C, nh, scale, s)
+e1.record()
+for _ in range(5):
+    _lib.call('og_flash_attn_bwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), nseq, S, C, nh, scale, s)
+e2.record(); torch.cuda.synchronize()
+tf, tb = e0.elapsed_time(e1) / 5, e1.elapsed_time(e2) / 5
+print(f'x5: fwd {tf:.3f} ms {fl / tf * 1e-9:.0f} TFLOP/s ; bwd {tb:.3f} ms {2.5 * fl / tb * 1e-9:.0f} TFLOP/s ; '
+      f'|dq| {dq.double().abs().sum().item():.6e} |dk| {dk.double().abs().sum().item():.6e} |dv| {dv.double().abs().sum().item():.6e}')
