@@ -606,12 +606,13 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
 // (~700 clk of a ~3400 clk iteration) and the MMAs idled during the softmax.
 // MODE 1 has no P tile in shared memory and uses the room for a third K/V stage.
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(kFaBwdThreads, 1)
+template <int MODE, int NW>   // NW softmax warps (8 or 16): 4 TMEM lane quarters x NW/4 column groups of 512/NW columns
+__global__ void __launch_bounds__(64 + 32 * NW, 1)
     og_flash_attn_bwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
                               const FaBwdParams p) {
   constexpr int kStages = MODE == 0 ? 2 : 3;
+  constexpr int CW = 512 / NW;  // columns of S / dP per softmax warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sFix = smem;                    // stationary pair: MODE 0: K_j, V_j ; MODE 1: Q_i, dO_i   (2 x 16 KiB)
@@ -649,8 +650,8 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     mbar_init(dp_full, 1);
-    mbar_init(dp_free, 8);
-    mbar_init(p_ready, 8);
+    mbar_init(dp_free, NW);
+    mbar_init(p_ready, NW);
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
@@ -787,9 +788,13 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
     if (elect_one()) umma_commit(acc_ready);
     __syncwarp();
   } else {
-    // 8 warps: warps w and w+4 share TMEM lane quarter (w & 3) and split the 128 columns of S / dP in halves.
+    // NW warps: warp w works on TMEM lane quarter (w & 3) (a hardware rule) and on column group (w - 2) / 4 of S / dP.
+    // The backward softmax has no cross-column reduction (lse and delta are per-row inputs), so the split is free.
+    // With 8 warps (2 per scheduler) the issue slots were 35-40 % busy: each warp stalls on MUFU / TMEM-load / fixed
+    // latencies with nothing else to issue; 16 warps hide them.
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cg = (warp - 2) >> 2;
+    const int c0 = cg * CW;
     const int row = qd * 32 + lane;  // TMEM lane: query row of the current pair
     const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
     const float cl2 = p.scale * 1.4426950408889634f;
@@ -826,13 +831,13 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
       const int kv_valid = p.S - kv_tile * kTile;
       const bool full = (q_tile + 1) * kTile <= p.S && kv_valid >= kTile;  // warp-uniform fast path
       const uint32_t tS = tS0 + ((it & 1) ? 128u : 0u);
-      float pf[64];
+      float pf[CW];
       // ---- phase A: probabilities from S(it)
       mbar_wait(&s_full[it & 1], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        const int c = half * 64 + cc;
+      for (int cc = 0; cc < CW; cc += 32) {
+        const int c = c0 + cc;
         uint32_t vs[32];
         tmem_ld_32x32(tS + lane_addr + c, vs);
         tmem_ld_wait();
@@ -862,23 +867,22 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
       // ---- phase B: dS from dP(it); the dP accumulator is handed back as soon as it sits in registers
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
-      uint32_t vd0[32], vd1[32];
-      tmem_ld_32x32(tDP + lane_addr + half * 64, vd0);
-      tmem_ld_32x32(tDP + lane_addr + half * 64 + 32, vd1);
+      uint32_t vd[CW / 32][32];
+#pragma unroll
+      for (int g = 0; g < CW / 32; ++g) tmem_ld_32x32(tDP + lane_addr + c0 + g * 32, vd[g]);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dp_free);
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        const int c = half * 64 + cc;
+      for (int cc = 0; cc < CW; cc += 32) {
+        const int c = c0 + cc;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           const int col = c + i;
           float df[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            df[e] = pf[cc + i + e] * (__uint_as_float(cc == 0 ? vd0[i + e] : vd1[i + e]) - delta);
+          for (int e = 0; e < 8; ++e) df[e] = pf[cc + i + e] * (__uint_as_float(vd[cc / 32][i + e]) - delta);
           uint4 u;
           u.x = pack_bf16x2(df[0], df[1]);
           u.y = pack_bf16x2(df[2], df[3]);
@@ -892,12 +896,13 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // accumulators complete: TMEM lane = output row (kv row in MODE 0, query row in MODE 1); the two warps of a
-    // lane quarter take 32 of the 64 columns each. dK / dQ carry the softmax scale here.
+    // accumulators complete: TMEM lane = output row (kv row in MODE 0, query row in MODE 1); two warps of a lane
+    // quarter take 32 of the 64 columns each. dK / dQ carry the softmax scale here.
     mbar_wait_relaxed(acc_ready, 0);
     tc_fence_after();
     const int orow = own * kTile + row;
-    for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
+    const int half = cg;
+    for (int a = 0; a < (cg >= 2 ? 0 : (MODE == 0 ? 2 : 1)); ++a) {
       __nv_bfloat16* base = MODE == 1 ? p.dq : (a == 0 ? p.dv : p.dk);
       const uint32_t tacc = a == 0 ? tAcc0 : tAcc1;
       const float osc = (MODE == 0 && a == 0) ? 1.f : p.scale;
@@ -1030,10 +1035,10 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
                                        (int)smem_bytes));
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
-    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes));
-    OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes));
+    const void* k2[] = {(const void*)og_flash_attn_bwd2_kernel<0, 8>, (const void*)og_flash_attn_bwd2_kernel<1, 8>,
+                        (const void*)og_flash_attn_bwd2_kernel<0, 16>, (const void*)og_flash_attn_bwd2_kernel<1, 16>};
+    for (const void* f : k2)
+      OG_CHECK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr = true;
   }
   const long long grid = (long long)nseq * n_head * p.tiles;
@@ -1048,9 +1053,17 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
     og_flash_attn_bwd_kernel<1><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
     OG_CHECK_CUDA(cudaGetLastError());
   } else {
-    og_flash_attn_bwd2_kernel<0><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
-    OG_CHECK_CUDA(cudaGetLastError());
-    og_flash_attn_bwd2_kernel<1><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+    static const int nw = [] {
+      const char* e = getenv("OG_FLASH_BWD_WARPS");   // 8 or 16 softmax warps
+      return (e && atoi(e) == 8) ? 8 : 16;
+    }();
+    if (nw == 8) {
+      og_flash_attn_bwd2_kernel<0, 8><<<(unsigned)grid, 64 + 32 * 8, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+      og_flash_attn_bwd2_kernel<1, 8><<<(unsigned)grid, 64 + 32 * 8, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+    } else {
+      og_flash_attn_bwd2_kernel<0, 16><<<(unsigned)grid, 64 + 32 * 16, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+      og_flash_attn_bwd2_kernel<1, 16><<<(unsigned)grid, 64 + 32 * 16, smem_bytes, s>>>(mq, mk, mv, mdo, p);
+    }
     OG_CHECK_CUDA(cudaGetLastError());
   }
   g_launches.fetch_add(2);
