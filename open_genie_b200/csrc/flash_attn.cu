@@ -42,6 +42,20 @@ __device__ __forceinline__ void st_swizzled_chunk(uint8_t* tile, int row, int ch
   *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
 }
 
+// Ordered variants (volatile asm keeps their relative program order): used to INTERLEAVE the MUFU exponentials of one
+// column chunk with the FMA / ALU / store work of the previous one — left alone, ptxas emits 32 MUFU.EX2 back to back
+// (8 clk each on the 4-lane XU pipe) and the other pipes idle meanwhile.
+__device__ __forceinline__ float ex2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void st_swizzled_chunk_ordered(uint8_t* tile, int row, int chunk, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(tile + row * 128 + ((chunk ^ (row & 7)) << 4))),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kFaThreads, 2)
     og_flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                              const __grid_constant__ CUtensorMap mapV, const FaParams p) {
@@ -332,6 +346,9 @@ __global__ void __launch_bounds__(kFaThreads, 2)
 // ------------------------------------------------------------------------------------------------
 struct FaBwdParams {
   int S, C, nh, nseq, tiles;
+  int interleave;  // bwd2, 8 softmax warps: interleave exponentials with the previous chunk's dS work
+  int dbg;         // timing experiments only (OG_FLASH_DBG; results are wrong): 1 = no MUFU.EX2, 2 = no P / dS smem stores,
+                   // 4 = no gradient MMAs, 8 = no S / dP MMAs, 32 = softmax warps run the barrier protocol only (+16: no TMEM loads), 64 = no TMA stream loads
   float scale;
   const float* lse;    // [nseq][nh][S]
   const float* delta;  // [nseq][nh][S]
@@ -604,31 +621,31 @@ __global__ void __launch_bounds__(kFaBwdThreads, 1)
 // MMA issue order per iteration:  dP(it) | dV,dK / dQ of it-1 | S(it+1).
 // In the first version the order was S,dP(it) -> softmax(it) -> S,dP(it+1): the softmax warps idled while S/dP ran
 // (~700 clk of a ~3400 clk iteration) and the MMAs idled during the softmax.
-// MODE 1 has no P tile in shared memory and uses the room for a third K/V stage.
+// MODE 1 has no P tile in shared memory and uses the room for four K/V stages instead of two.
 // ------------------------------------------------------------------------------------------------
 template <int MODE, int NW>   // NW softmax warps (8 or 16): 4 TMEM lane quarters x NW/4 column groups of 512/NW columns
 __global__ void __launch_bounds__(64 + 32 * NW, 1)
     og_flash_attn_bwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                               const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
                               const FaBwdParams p) {
-  constexpr int kStages = MODE == 0 ? 2 : 3;
+  constexpr int kStages = MODE == 0 ? 2 : 4;
   constexpr int CW = 512 / NW;  // columns of S / dP per softmax warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sFix = smem;                    // stationary pair: MODE 0: K_j, V_j ; MODE 1: Q_i, dO_i   (2 x 16 KiB)
-  uint8_t* sStr = smem + 2 * kTileBytes;   // streamed pair, kStages x (2 x 16 KiB)   (MODE 1: runs into the P region)
+  uint8_t* sStr = smem + 2 * kTileBytes;   // streamed pair, kStages x (2 x 16 KiB)   (MODE 1: covers the unused P region)
   uint8_t* sP = smem + 6 * kTileBytes;     // P  bf16 [2 buffers][2 k-blocks][128][128 B]   (MODE 0 only)
   uint8_t* sDS = smem + 10 * kTileBytes;   // dS bf16, same shape
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * kTileBytes);
   uint64_t* fix_full = bars;
-  uint64_t* str_full = bars + 1;   // [3]
-  uint64_t* str_empty = bars + 4;  // [3]
-  uint64_t* s_full = bars + 7;     // [2]
-  uint64_t* dp_full = bars + 9;
-  uint64_t* dp_free = bars + 10;
-  uint64_t* p_ready = bars + 11;
-  uint64_t* acc_ready = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* str_full = bars + 1;   // [4]
+  uint64_t* str_empty = bars + 5;  // [4]
+  uint64_t* s_full = bars + 9;     // [2]
+  uint64_t* dp_full = bars + 11;
+  uint64_t* dp_free = bars + 12;
+  uint64_t* p_ready = bars + 13;
+  uint64_t* acc_ready = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   int id = blockIdx.x;
@@ -643,7 +660,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1)
     tma_prefetch_desc(&mapV);
     tma_prefetch_desc(&mapDO);
     mbar_init(fix_full, 1);
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&str_full[s], 1);
       mbar_init(&str_empty[s], 1);
     }
@@ -678,7 +695,9 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1)
     uint32_t ph = 1;   // the first pass over the ring finds every slot free
     for (int it = 0; it < p.tiles; ++it) {
       mbar_wait(&str_empty[st], ph);
-      if (elect_one()) {
+      if (p.dbg & 64) {
+        if (elect_one()) mbar_arrive(&str_full[st]);
+      } else if (elect_one()) {
         mbar_expect_tx(&str_full[st], 2 * kTileBytes);
         uint8_t* d = sStr + st * 2 * kTileBytes;
         if (MODE == 0) {
@@ -729,7 +748,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1)
         const uint32_t do_addr = (MODE == 0 ? stra : fixa) + kTileBytes, v_addr = (MODE == 0 ? fixa : stra) + kTileBytes;
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
+          for (int k = 0; k < ((p.dbg & 8) ? 0 : kD / 16); ++k)
             umma_bf16_ss(tDP, umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
                          umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
           umma_commit(dp_full);
@@ -742,7 +761,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1)
         tc_fence_after();
         const uint32_t stra = str0 + st_prev * 2 * kTileBytes;
         const uint32_t p_addr = p_base + (jj & 1) * 2 * kTileBytes, ds_addr = ds_base + (jj & 1) * 2 * kTileBytes;
-        if (!elect_one()) {
+        if (!elect_one() || (p.dbg & 4)) {
         } else if (MODE == 0) {
           const uint32_t q_addr = stra, do_addr = stra + kTileBytes;
 #pragma unroll
@@ -771,7 +790,7 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1)
         const uint32_t tS = tS0 + (((it + 1) & 1) ? 128u : 0u);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
+          for (int k = 0; k < ((p.dbg & 8) ? 0 : kD / 16); ++k)
             umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
                          umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
           umma_commit(&s_full[(it + 1) & 1]);
@@ -835,6 +854,102 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1)
       // ---- phase A: probabilities from S(it)
       mbar_wait(&s_full[it & 1], (it >> 1) & 1);
       tc_fence_after();
+      if (p.dbg & 32) {  // barrier protocol only
+        mbar_wait(dp_full, it & 1);
+        tc_fence_after();
+        if (!(p.dbg & 16)) {
+          uint32_t vs[32];
+          tmem_ld_32x32(tS + lane_addr + c0, vs);
+          tmem_ld_32x32(tDP + lane_addr + c0, vs);
+          tmem_ld_32x32(tS + lane_addr + c0 + 32, vs);
+          tmem_ld_32x32(tDP + lane_addr + c0 + 32, vs);
+          tmem_ld_wait();
+          if (vs[0] == 0x12345678u) pf[0] = 1.f;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_free);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        continue;
+      }
+      if (NW == 8 && full && p.interleave) {
+        // two 32-column chunks per warp: exps(chunk 0) | exps(chunk 1) interleaved with the dS (and P) work of chunk 0 |
+        // dS (and P) of chunk 1. Every 8 MUFU.EX2 are followed by the ~30 FMA / ALU / store instructions of 8 finished
+        // elements, which issue while the XU pipe works its queue off.
+        uint32_t vs[32], vd[32];
+        tmem_ld_32x32(tS + lane_addr + c0, vs);
+        tmem_ld_wait();
+        if (p.dbg & 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pf[i] = fmaf(__uint_as_float(vs[i]), cl2, -lse2);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pf[i] = ex2_approx(fmaf(__uint_as_float(vs[i]), cl2, -lse2));
+        }
+        mbar_wait(dp_full, it & 1);
+        tc_fence_after();
+        tmem_ld_32x32(tDP + lane_addr + c0, vd);
+        tmem_ld_32x32(tS + lane_addr + c0 + 32, vs);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float x = fmaf(__uint_as_float(vs[i + e]), cl2, -lse2);
+            pf[32 + i + e] = (p.dbg & 1) ? x : ex2_ordered(x);
+          }
+          const int col = c0 + i;
+          uint4 u;
+          if (MODE == 0) {
+            u.x = pack_bf16x2(pf[i], pf[i + 1]);
+            u.y = pack_bf16x2(pf[i + 2], pf[i + 3]);
+            u.z = pack_bf16x2(pf[i + 4], pf[i + 5]);
+            u.w = pack_bf16x2(pf[i + 6], pf[i + 7]);
+            if (!(p.dbg & 2)) st_swizzled_chunk_ordered(sP + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
+          }
+          float df[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) df[e] = pf[i + e] * (__uint_as_float(vd[i + e]) - delta);
+          u.x = pack_bf16x2(df[0], df[1]);
+          u.y = pack_bf16x2(df[2], df[3]);
+          u.z = pack_bf16x2(df[4], df[5]);
+          u.w = pack_bf16x2(df[6], df[7]);
+          if (!(p.dbg & 2)) st_swizzled_chunk_ordered(sDS + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
+        }
+        tmem_ld_32x32(tDP + lane_addr + c0 + 32, vd);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_free);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const int col = c0 + 32 + i;
+          uint4 u;
+          if (MODE == 0) {
+            u.x = pack_bf16x2(pf[32 + i], pf[32 + i + 1]);
+            u.y = pack_bf16x2(pf[32 + i + 2], pf[32 + i + 3]);
+            u.z = pack_bf16x2(pf[32 + i + 4], pf[32 + i + 5]);
+            u.w = pack_bf16x2(pf[32 + i + 6], pf[32 + i + 7]);
+            st_swizzled_chunk(sP + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
+          }
+          float df[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) df[e] = pf[32 + i + e] * (__uint_as_float(vd[i + e]) - delta);
+          u.x = pack_bf16x2(df[0], df[1]);
+          u.y = pack_bf16x2(df[2], df[3]);
+          u.z = pack_bf16x2(df[4], df[5]);
+          u.w = pack_bf16x2(df[6], df[7]);
+          st_swizzled_chunk(sDS + ((it & 1) * 2 + (col >> 6)) * kTileBytes, row, (col & 63) >> 3, u);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+        continue;
+      }
 #pragma unroll
       for (int cc = 0; cc < CW; cc += 32) {
         const int c = c0 + cc;
@@ -1053,9 +1168,19 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
     og_flash_attn_bwd_kernel<1><<<(unsigned)grid, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p);
     OG_CHECK_CUDA(cudaGetLastError());
   } else {
+    static const int il = [] {
+      const char* e = getenv("OG_FLASH_BWD_INTERLEAVE");
+      return (e && atoi(e) == 0) ? 0 : 1;
+    }();
+    p.interleave = il;
+    static const int dbg = [] {
+      const char* e = getenv("OG_FLASH_DBG");
+      return e ? atoi(e) : 0;
+    }();
+    p.dbg = dbg;
     static const int nw = [] {
       const char* e = getenv("OG_FLASH_BWD_WARPS");   // 8 or 16 softmax warps
-      return (e && atoi(e) == 8) ? 8 : 16;
+      return (e && atoi(e) == 16) ? 16 : 8;
     }();
     if (nw == 8) {
       og_flash_attn_bwd2_kernel<0, 8><<<(unsigned)grid, 64 + 32 * 8, smem_bytes, s>>>(mq, mk, mv, mdo, p);
