@@ -107,13 +107,15 @@ def usable_cores():
 
 
 def pick_cpu_threads():
-    """Thread policy of the CPU arm, stated in the JSON line: the thread count (powers of two up to the usable cores,
-    plus the usable core count itself) that runs a conv3d forward+backward probe fastest — best of 3 repetitions each,
-    every candidate's time recorded. On a shared 128-core host all 128 threads are an order of magnitude SLOWER than 32
-    (oversubscription), so `os.cpu_count()` threads would flatter the GPU/CPU ratio; the fastest setting is the fair one."""
+    """Thread policy of the CPU arm, stated in the JSON line: a FIXED min(32, usable cores) threads (OG_CPU_THREADS
+    overrides). Measured on this pool's 128-thread hosts with the whole reference training step: 32 threads 1.99-2.27
+    frames/s, 64 threads 1.32 frames/s (profiles/r02bb_*), and with all 128 threads a conv3d probe is 25-50x slower
+    (oversubscription) — so `os.cpu_count()` threads would flatter the GPU/CPU ratio. Earlier rounds PICKED the count with
+    a conv3d probe; the probe put 32 and 64 within 5 % of each other and flipped between runs, so it is now reported
+    only (`thread_probe_ms`, conv3d forward+backward, best of 3) and no longer decides."""
     import torch.nn.functional as F
     avail = usable_cores()
-    cands = sorted({c for c in (4, 8, 16, 32, 64, 128, avail) if c <= avail})
+    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail})
     x = torch.randn(1, 128, 8, 64, 64, requires_grad=True)
     w = torch.randn(128, 128, 3, 3, 3, requires_grad=True)
     probe = {}
@@ -126,7 +128,8 @@ def pick_cpu_threads():
             F.conv3d(x, w, padding=1).sum().backward()
             best = min(best, time.perf_counter() - t0)
         probe[c] = round(best * 1e3, 1)
-    pick = min(probe, key=probe.get)
+    env = os.environ.get('OG_CPU_THREADS')
+    pick = max(1, min(int(env), avail)) if env else min(32, avail)
     torch.set_num_threads(pick)
     return pick, avail, probe
 
@@ -186,8 +189,8 @@ WORKLOAD = ('BASELINE configs[1]: MAGVIT2_ENC/DEC VideoTokenizer training step (
 def cpu_sample_text(batch, threads, avail, kind):
     what = ('unmodified reference package (baseline/_ref) through its own VideoTokenizer.training_step + AdamW'
             if kind == 'reference' else 'oracle/genie_oracle.py port of the reference (pinned to reference outputs)')
-    return (f'{batch} clip(s) x {FRAMES} frames per step, fp32 torch CPU, {threads} threads (fastest on a conv3d probe among '
-            f'the {avail} usable cores); {what}')
+    return (f'{batch} clip(s) x {FRAMES} frames per step, fp32 torch CPU, {threads} threads (fixed policy min(32, cores): '
+            f'the fastest count for this step on the {avail}-thread hosts, 64 threads measured 1.5x slower); {what}')
 
 
 def run_reference(args, rank, world):
