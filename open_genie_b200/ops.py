@@ -210,6 +210,30 @@ FUSE_STATS = _os.environ.get('OG_FUSE_STATS', '1') != '0'
 FUSE_RED = _os.environ.get('OG_FUSE_RED', '0') != '0'   # measured: costs more in the dgrad epilogue than the pass it saves
 
 
+# GroupNorm backward over sample GROUPS: reduce(group) then apply(group), so that the apply pass finds the group's dy / x in
+# L2 (126 MB) instead of streaming them from HBM a second time. Only for tensors that do not fit L2 as a whole; groups run
+# from the last sample to the first because the producing data-gradient kernel wrote the last samples last (still in L2).
+GN_BWD_GROUPS = int(_os.environ.get('OG_GN_BWD_GROUPS', '1'))
+GN_BWD_MIN_BYTES = int(_os.environ.get('OG_GN_BWD_MIN_MB', '96')) << 20
+
+
+def _gn_bwd(dy, x, A, Bc, S, mr, gamma, beta, G, act, add, dx, dgamma, dbeta, dx_colsum, B, V, C, s, reduce=True):
+    """og_affine_act_bwd_reduce + og_gn_act_bwd on bf16 [B, V, C] tensors (the ResidualBlock's GroupNorm(1, C) / SiLU
+    backward, genie/module/video.py:607-629), optionally split over sample groups (see GN_BWD_GROUPS)."""
+    groups = GN_BWD_GROUPS if (GN_BWD_GROUPS > 1 and B % GN_BWD_GROUPS == 0 and 2 * B * V * C >= GN_BWD_MIN_BYTES) else 1
+    nb = B // groups
+    for g in reversed(range(groups)):
+        n0 = g * nb
+        oa, oc, oS, om = n0 * V * C * 2, n0 * C * 4, n0 * C * 8, n0 * G * 8
+        if reduce:
+            _lib.call('og_affine_act_bwd_reduce', dy.data_ptr() + oa, x.data_ptr() + oa, A.data_ptr() + oc, Bc.data_ptr() + oc,
+                      act, S.data_ptr() + oS, nb, V, C, s)
+        _lib.call('og_gn_act_bwd', dy.data_ptr() + oa, x.data_ptr() + oa, A.data_ptr() + oc, Bc.data_ptr() + oc,
+                  S.data_ptr() + oS, mr.data_ptr() + om, gamma.data_ptr(), beta.data_ptr(), None, G, act,
+                  (add.data_ptr() + oa) if add is not None else None, dx.data_ptr() + oa, dgamma.data_ptr(), dbeta.data_ptr(),
+                  None, None, dx_colsum.data_ptr() if dx_colsum is not None else None, nb, V, C, s)
+
+
 def _workspace(dev, nbytes: int):
     """Reusable fp32 scratch for split-K convolutions (small T*H*W, deep K). One buffer per device and step scope;
     every use is stream-ordered (memset -> partial sums -> finish pass inside one og_conv3d_* call)."""
@@ -1271,19 +1295,20 @@ class _ResBlockFn(torch.autograd.Function):
                    ld2, 0, geom2.kt, geom2.kh, geom2.kw, geom2.pt, geom2.ph, geom2.pw, d_a2.data_ptr(), 0, B, T, H, W, C1,
                    ws.data_ptr(), ws.numel(), *((h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), act, S2.data_ptr())
                                                 if FUSE_RED else (None, None, None, 0, None)), s)
-        if not FUSE_RED:
-            _lib.call('og_affine_act_bwd_reduce', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), act,
-                      S2.data_ptr(), B, V, C1, s)
         small = _zeros((3, C1), f32, dev)              # dgamma2, dbeta2, db1 in one fill
         dg2w, dg2b, db1 = small[0], small[1], small[2]
         d_h1 = empty_internal(B, C1, T, H, W, bf16, dev)
-        _lib.call('og_gn_act_bwd', d_a2.data_ptr(), h1.data_ptr(), A2.data_ptr(), B2.data_ptr(), S2.data_ptr(),
-                  mr[1].data_ptr(), g2w.data_ptr(), g2b.data_ptr(), None, G, act, None, d_h1.data_ptr(), dg2w.data_ptr(),
-                  dg2b.data_ptr(), None, None, db1.data_ptr() if has_b1 else None, B, V, C1, s)
+        _gn_bwd(d_a2, h1, A2, B2, S2, mr[1], g2w, g2b, G, act, None, d_h1, dg2w, dg2b, db1 if has_b1 else None, B, V, C1, s,
+                reduce=not FUSE_RED)
         dw1 = wgrad(d_h1, C1, a1, C0, geom1)
         dx = None
         dg1w, dg1b = _zeros(C0, f32, dev), _zeros(C0, f32, dev)
-        # conv1 data gradient + fused GN1 backward reduction; shortcut data gradient; GN1 backward apply adds both
+        # shortcut data gradient first, so that GN1's reduce / apply passes follow the conv1 data gradient directly
+        dx_res = empty_internal(B, C0, T, H, W, bf16, dev)
+        _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
+                   geom2.k_main, 1, 1, 1, 0, 0, 0, dx_res.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
+                   None, None, None, 0, None, s)
+        # conv1 data gradient (+ fused GN1 backward reduction); GN1 backward apply adds the shortcut gradient
         S1 = _zeros((B, C0, 2), f32, dev)
         d_a1 = empty_internal(B, C0, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_dgrad', d_h1.data_ptr(), C1, C1,
@@ -1291,18 +1316,10 @@ class _ResBlockFn(torch.autograd.Function):
                    d_a1.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
                    *((xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), act, S1.data_ptr()) if FUSE_RED
                      else (None, None, None, 0, None)), s)
-        if not FUSE_RED:
-            _lib.call('og_affine_act_bwd_reduce', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), act,
-                      S1.data_ptr(), B, V, C0, s)
-        dx_res = empty_internal(B, C0, T, H, W, bf16, dev)
-        _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
-                   geom2.k_main, 1, 1, 1, 0, 0, 0, dx_res.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
-                   None, None, None, 0, None, s)
         # (the input gradient is always produced: its pass is also what emits dgamma1 / dbeta1)
         dx = empty_internal(B, C0, T, H, W, bf16, dev)
-        _lib.call('og_gn_act_bwd', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), S1.data_ptr(),
-                  mr[0].data_ptr(), g1w.data_ptr(), g1b.data_ptr(), None, G, act, dx_res.data_ptr(), dx.data_ptr(),
-                  dg1w.data_ptr(), dg1b.data_ptr(), None, None, None, B, V, C0, s)
+        _gn_bwd(d_a1, xi, A1, B1, S1, mr[0], g1w, g1b, G, act, dx_res, dx, dg1w, dg1b, None, B, V, C0, s,
+                reduce=not FUSE_RED)
         return (dx, None, dg1w, dg1b, dw1, db1 if has_b1 else None, dg2w, dg2b, dw2, db2 if has_b2 else None, dwres,
                 (db2.clone() if has_b2 else db2) if has_bres else None, None, None, None, None, None, None, None)
 
