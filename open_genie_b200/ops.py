@@ -1303,12 +1303,17 @@ class _ResBlockFn(torch.autograd.Function):
         dw1 = wgrad(d_h1, C1, a1, C0, geom1)
         dx = None
         dg1w, dg1b = _zeros(C0, f32, dev), _zeros(C0, f32, dev)
-        # shortcut data gradient first, so that GN1's reduce / apply passes follow the conv1 data gradient directly
         dx_res = empty_internal(B, C0, T, H, W, bf16, dev)
-        _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
-                   geom2.k_main, 1, 1, 1, 0, 0, 0, dx_res.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
-                   None, None, None, 0, None, s)
-        # conv1 data gradient (+ fused GN1 backward reduction); GN1 backward apply adds the shortcut gradient
+
+        def shortcut_dgrad():
+            _conv_call('dgrad', 2.0 * B * V * C1 * C0, 'og_conv3d_dgrad', dyb.data_ptr(), C1, C1, packed2.data_ptr(), ld2,
+                       geom2.k_main, 1, 1, 1, 0, 0, 0, dx_res.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
+                       None, None, None, 0, None, s)
+
+        grouped = GN_BWD_GROUPS > 1      # reduce + apply per sample group must be adjacent: the shortcut gradient goes first
+        if grouped:
+            shortcut_dgrad()
+        # conv1 data gradient (+ fused GN1 backward reduction); shortcut data gradient; GN1 backward apply adds both
         S1 = _zeros((B, C0, 2), f32, dev)
         d_a1 = empty_internal(B, C0, T, H, W, bf16, dev)
         _conv_call('dgrad', 2.0 * B * V * C1 * geom1.k_main, 'og_conv3d_dgrad', d_h1.data_ptr(), C1, C1,
@@ -1316,10 +1321,15 @@ class _ResBlockFn(torch.autograd.Function):
                    d_a1.data_ptr(), 0, B, T, H, W, C0, ws.data_ptr(), ws.numel(),
                    *((xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), act, S1.data_ptr()) if FUSE_RED
                      else (None, None, None, 0, None)), s)
+        if not grouped:
+            if not FUSE_RED:
+                _lib.call('og_affine_act_bwd_reduce', d_a1.data_ptr(), xi.data_ptr(), A1.data_ptr(), B1.data_ptr(), act,
+                          S1.data_ptr(), B, V, C0, s)
+            shortcut_dgrad()
         # (the input gradient is always produced: its pass is also what emits dgamma1 / dbeta1)
         dx = empty_internal(B, C0, T, H, W, bf16, dev)
         _gn_bwd(d_a1, xi, A1, B1, S1, mr[0], g1w, g1b, G, act, dx_res, dx, dg1w, dg1b, None, B, V, C0, s,
-                reduce=not FUSE_RED)
+                reduce=grouped and not FUSE_RED)
         return (dx, None, dg1w, dg1b, dw1, db1 if has_b1 else None, dg2w, dg2b, dw2, db2 if has_b2 else None, dwres,
                 (db2.clone() if has_b2 else db2) if has_bres else None, None, None, None, None, None, None, None)
 
