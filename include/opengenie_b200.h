@@ -104,6 +104,14 @@ int og_conv3d_dgrad(const void* dy, int cout, int w_rows, const void* w, int ldw
  * tap-major / channel-minor inside a row (the channels_last_3d order of the torch weight). */
 int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt, int kh,
                     int kw, int pt, int ph, int pw, int N, int T, int H, int W, og_stream_t stream);
+/* og_conv3d_wgrad + the bias gradient of the same nn.Conv3d in one launch: dbias[c] += sum over voxels of dy[v][c] for
+ * c < n_bias (1 <= n_bias <= cout; caller zeroes dbias). The sums come out of the same tensor-core pass (an extra N = 16
+ * product against a tile of ones in the last filter-tap group); when the tiling leaves no spare accumulator columns the
+ * call runs og_colsum afterwards — same result either way. Replaces the bias half of autograd's conv3d backward
+ * (genie/module/video.py:178-192, 609-629). */
+int og_conv3d_wgrad_bias(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt, int kh,
+                         int kw, int pt, int ph, int pw, int N, int T, int H, int W, float* dbias, int n_bias,
+                         og_stream_t stream);
 
 /* Strided CausalConv3d — SpaceTimeDownsample (genie/module/video.py:457-483) — as the SAME implicit GEMM, no im2col:
  * geometry of video.py:154-164 (time padded at the FRONT only by pt = (kt-1) + (1-st); space symmetrically by

@@ -10,6 +10,10 @@
 // accumulator block in TMEM (up to 4 taps x 128 columns = all 512 columns); the dY tile of a k-step is
 // loaded once and reused by every tap of the group. The voxel range is split across CTAs (split-K) and
 // partial sums are combined with fp32 red.global.add into dW, which the caller zeroes.
+// Optional fused bias gradient (og_conv3d_wgrad_bias): db[co] = sum_v dY[v][co] is the same GEMM against a column of
+// ones — the CTAs of the LAST tap group (which has accumulator columns to spare whenever ntaps % 4 != 0 or Cin tiles are
+// 64 wide) issue one extra N = 16 MMA per k-step against a constant all-ones tile in shared memory (a tile of ones is
+// invariant under the 128-byte swizzle, so any valid descriptor reads it correctly); 4 of ~100 MMAs, no extra pass over dY.
 //
 // Replaces autograd's conv3d weight-gradient reached from genie/module/video.py:192,609-629,599-603 and
 // genie/module/attention.py:429-438 during loss.backward().
@@ -34,6 +38,9 @@ struct WgradParams {
   int a_stages, b_stages;
   int sx_t, sx_h, sx_w;  // X box start = dY box start * stride + tap offset (strided convolution; 1 otherwise)
   int vec_ok;  // dw rows 16-byte aligned: vector reductions
+  float* dbias;     // optional: += column sums of dY for output channels < n_bias (the convolution's bias gradient)
+  int n_bias;
+  int bias_col;     // TMEM column of the 16-wide ones-product block (last tap group only)
   int plain_store;  // OG_WGRAD_PLAIN_STORE=1: the ABI says "accumulates", so overwriting is opt-in (the Python side zeroes dw anyway)
   int dbg;     // timing experiments only (OG_WGRAD_DBG): 1 = pretend A is K-major, 2 = pretend B is K-major, 4 = skip epilogue
 };
@@ -56,7 +63,8 @@ __global__ void __launch_bounds__(kWThreads, 1)
   const int b_bytes = 2 * tap_bytes;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.a_stages * kWABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.b_stages * b_bytes);
+  uint8_t* smem_ones = smem_b + p.b_stages * b_bytes;   // 16 k-rows x 128 B of bf16 1.0 (bias-gradient operand), 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + 2048);
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + kWMaxStages;
   uint64_t* full_b = bars + 2 * kWMaxStages;
@@ -74,6 +82,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
   const int group = blockIdx.z - split * p.num_groups;
   const int tap0 = group * p.taps_per_group;
   const int ntap = min(p.taps_per_group, p.ntaps - tap0);
+  const bool do_bias = p.dbias != nullptr && blockIdx.y == 0 && group == p.num_groups - 1;
   // contiguous k-step range of this split
   const int ks_begin = (int)(((long long)p.num_ksteps * split) / p.splitk);
   const int ks_end = (int)(((long long)p.num_ksteps * (split + 1)) / p.splitk);
@@ -93,6 +102,10 @@ __global__ void __launch_bounds__(kWThreads, 1)
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (do_bias) {
+    for (int i = threadIdx.x; i < 2048 / 4; i += kWThreads) reinterpret_cast<uint32_t*>(smem_ones)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -177,6 +190,7 @@ __global__ void __launch_bounds__(kWThreads, 1)
       const uint32_t amn = (p.dbg & 1) ? 0u : 1u, bmn = (p.dbg & 2) ? 0u : 1u;
       const uint32_t idesc1 = umma_idesc_bf16(128, (uint32_t)p.block_n, amn, bmn);
       const uint32_t idesc2 = umma_idesc_bf16(128, (uint32_t)(2 * p.block_n), amn, bmn);
+      const uint32_t idesc_ones = umma_idesc_bf16(128, 16u, amn, 1u);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       for (int ks = ks_begin; ks < ks_end; ++ks) {
@@ -205,6 +219,14 @@ __global__ void __launch_bounds__(kWThreads, 1)
             phb ^= 1;
           }
         }
+        if (do_bias && elect_one()) {   // db += dY^T . 1  (N = 16 columns of ones; every column holds the same sum)
+          const uint32_t ones_addr = smem_u32(smem_ones);
+#pragma unroll
+          for (int k = 0; k < kVox / 16; ++k)
+            umma_bf16_ss(tmem_base + p.bias_col, umma_smem_desc_sw128(a_addr + k * 2048, kPanelBytes, 1024),
+                         umma_smem_desc_sw128(ones_addr, kPanelBytes, 1024), idesc_ones, (ks > ks_begin || k > 0) ? 1u : 0u);
+        }
+        __syncwarp();
         if (elect_one()) umma_commit(&empty_a[sa]);
         __syncwarp();
         if (++sa == p.a_stages) {
@@ -253,6 +275,12 @@ __global__ void __launch_bounds__(kWThreads, 1)
         }
       }
     }
+    if (do_bias) {
+      uint32_t v[16];
+      tmem_ld_32x16(tmem_base + p.bias_col + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_wait();
+      if (co < p.n_bias) atomicAdd(p.dbias + co, __uint_as_float(v[0]));
+    }
     tc_fence_before();
   }
 
@@ -269,9 +297,10 @@ __global__ void __launch_bounds__(kWThreads, 1)
 // N,T,H,W: the dY grid (= output voxels). Ti,Hi,Wi / st,sh,sw: extents of x and the convolution strides.
 static int launch_wgrad(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt, int kh, int kw,
                         int pt, int ph, int pw, int N, int T, int H, int W, int Ti, int Hi, int Wi, int st, int sh, int sw,
-                        og_stream_t stream) {
+                        og_stream_t stream, float* dbias = nullptr, int n_bias = 0) {
   using namespace og;
   OG_REQUIRE(dy && x && dw, "conv3d_wgrad: null pointer");
+  OG_REQUIRE(!dbias || (n_bias > 0 && n_bias <= cout), "conv3d_wgrad: n_bias=%d must be in 1..cout", n_bias);
   OG_REQUIRE(cin > 0 && cin % 64 == 0, "conv3d_wgrad: cin=%d must be a multiple of 64", cin);
   OG_REQUIRE(cout > 0 && cout % 8 == 0, "conv3d_wgrad: cout=%d must be a multiple of 8 (TMA row stride)", cout);
   OG_REQUIRE(kt >= 1 && kh >= 1 && kw >= 1 && pt >= 0 && ph >= 0 && pw >= 0 && pt < kt && ph < kh && pw < kw,
@@ -323,11 +352,23 @@ static int launch_wgrad(const void* dy, int cout, const void* x, int cin, float*
     p.plain_store = ps ? atoi(ps) : 0;
   }
   p.vec_ok = (ld_dw % 4 == 0) && (cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(dw) & 15) == 0);
+  // fused bias gradient: the last tap group needs 16 spare accumulator columns
+  bool colsum_after = false;
+  if (dbias) {
+    const int ntap_last = p.ntaps - (p.num_groups - 1) * p.taps_per_group;
+    if (ntap_last * p.block_n + 16 <= 512 && !(p.dbg & 3)) {
+      p.dbias = dbias;
+      p.n_bias = n_bias;
+      p.bias_col = ntap_last * p.block_n;
+    } else {
+      colsum_after = true;   // 4 full 128-wide tap blocks: no room — separate pass over dY
+    }
+  }
   const int b_bytes = 2 * (p.block_n / 64) * kPanelBytes;  // a pair of taps per stage
   p.a_stages = 3;
   p.b_stages = (int)((216 * 1024 - p.a_stages * kWABytes) / b_bytes);
   if (p.b_stages > kWMaxStages) p.b_stages = kWMaxStages;
-  const size_t smem_bytes = (size_t)p.a_stages * kWABytes + (size_t)p.b_stages * b_bytes + 1024 + 512;
+  const size_t smem_bytes = (size_t)p.a_stages * kWABytes + (size_t)p.b_stages * b_bytes + 2048 /*ones*/ + 1024 + 512;
 
   CUtensorMap mapDY, mapX;
   {
@@ -358,6 +399,7 @@ static int launch_wgrad(const void* dy, int cout, const void* x, int cin, float*
   og_conv_wgrad_kernel<<<grid, kWThreads, smem_bytes, (cudaStream_t)stream>>>(mapDY, mapX, p);
   OG_CHECK_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
+  if (colsum_after) return og_colsum(dy, (int64_t)N * T * H * W, n_bias, cout, dbias, stream);
   return OG_OK;
 }
 
@@ -365,6 +407,19 @@ extern "C" int og_conv3d_wgrad(const void* dy, int cout, const void* x, int cin,
                                int kh, int kw, int pt, int ph, int pw, int N, int T, int H, int W,
                                og_stream_t stream) {
   return launch_wgrad(dy, cout, x, cin, dw, ld_dw, kt, kh, kw, pt, ph, pw, N, T, H, W, T, H, W, 1, 1, 1, stream);
+}
+
+// Weight gradient + bias gradient in one launch: dbias[c] += sum over voxels of dy[v][c] for c < n_bias (the bias
+// gradient of the same nn.Conv3d); see the file header. Falls back to an og_colsum pass when the tiling has no spare
+// accumulator columns.
+extern "C" int og_conv3d_wgrad_bias(const void* dy, int cout, const void* x, int cin, float* dw, int64_t ld_dw, int kt,
+                                    int kh, int kw, int pt, int ph, int pw, int N, int T, int H, int W, float* dbias,
+                                    int n_bias, og_stream_t stream) {
+  if (!dbias) {
+    og::set_error("conv3d_wgrad_bias: dbias is NULL");
+    return OG_ERR_INVALID_ARGUMENT;
+  }
+  return launch_wgrad(dy, cout, x, cin, dw, ld_dw, kt, kh, kw, pt, ph, pw, N, T, H, W, T, H, W, 1, 1, 1, stream, dbias, n_bias);
 }
 
 // Weight gradient of the strided CausalConv3d (SpaceTimeDownsample): dy on the OUTPUT grid, x on the input grid

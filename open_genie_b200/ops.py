@@ -208,6 +208,7 @@ def _zeros(shape, dtype, device, recording: bool = False):
 import os as _os
 FUSE_STATS = _os.environ.get('OG_FUSE_STATS', '1') != '0'
 FUSE_RED = _os.environ.get('OG_FUSE_RED', '0') != '0'   # measured: costs more in the dgrad epilogue than the pass it saves
+FUSE_BIAS_GRAD = _os.environ.get('OG_FUSE_BIAS_GRAD', '1') != '0'   # bias gradient inside the weight-gradient launch
 
 
 # GroupNorm backward over sample GROUPS: reduce(group) then apply(group), so that the apply pass finds the group's dy / x in
@@ -478,14 +479,24 @@ class _Conv3dFn(torch.autograd.Function):
         dev = dy.device
         ws = _workspace(dev, B * T * H * W * max(C, 64) * 4)
 
+        want_db = (ctx.has_bias[0] and need[2]) or (ctx.has_bias[1] and need[5])
+        dbs = _zeros(cout, f32, dev) if want_db else None
+        fused_db = [False]
+
         def wgrad(xin, cin, kt, kh, kw, pt, ph, pw, shape5, dims):
-            """fp32 gradient with the parameter's channels_last_3d memory: [cout][tap][cin]."""
+            """fp32 gradient with the parameter's channels_last_3d memory: [cout][tap][cin]. The first weight gradient of
+            this backward also produces the bias gradient (column sums of dy) when one is wanted."""
             rows = cpad if cpad != cout else cout
             g = _zeros((rows, kt * kh * kw * cin), f32, dev)
             real_cin = C if (geom.padded and cin == geom.cin_pad) else cin      # algorithmic FLOPs: no padding counted
-            _conv_call('wgrad', 2.0 * dims[0] * dims[1] * dims[2] * dims[3] * cout * min(real_cin, geom.k_main) * kt * kh * kw,
-                       'og_conv3d_wgrad', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(), g.shape[1],
-                      kt, kh, kw, pt, ph, pw, dims[0], dims[1], dims[2], dims[3], s)
+            fl = 2.0 * dims[0] * dims[1] * dims[2] * dims[3] * cout * min(real_cin, geom.k_main) * kt * kh * kw
+            if want_db and FUSE_BIAS_GRAD and not fused_db[0]:
+                fused_db[0] = True
+                _conv_call('wgrad', fl, 'og_conv3d_wgrad_bias', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(),
+                           g.shape[1], kt, kh, kw, pt, ph, pw, dims[0], dims[1], dims[2], dims[3], dbs.data_ptr(), cout, s)
+            else:
+                _conv_call('wgrad', fl, 'og_conv3d_wgrad', dyb.data_ptr(), cpad, xin.data_ptr(), cin, g.data_ptr(), g.shape[1],
+                           kt, kh, kw, pt, ph, pw, dims[0], dims[1], dims[2], dims[3], s)
             return g[:cout]
 
         Cp = geom.cin_pad
@@ -540,9 +551,9 @@ class _Conv3dFn(torch.autograd.Function):
             if need[1]:
                 g = wgrad(col, geom.kpad, 1, 1, 1, 0, 0, 0, ctx.w_shapes[0], (1, 1, 1, B * To * Ho * Wo))
                 dw = g[:, :geom.k_main].reshape(cout, geom.kt, geom.kh, geom.kw, C).permute(0, 4, 1, 2, 3)
-        if (ctx.has_bias[0] and need[2]) or (ctx.has_bias[1] and need[5]):
-            dbs = _zeros(cout, f32, dev)
-            _lib.call('og_colsum', dyb.data_ptr(), B * To * Ho * Wo, cout, cpad, dbs.data_ptr(), s)
+        if want_db:
+            if not fused_db[0]:
+                _lib.call('og_colsum', dyb.data_ptr(), B * To * Ho * Wo, cout, cpad, dbs.data_ptr(), s)
             if ctx.has_bias[0] and need[2]:
                 db = dbs
             if ctx.has_bias[1] and need[5]:
@@ -1277,17 +1288,23 @@ class _ResBlockFn(torch.autograd.Function):
         ws = _workspace(dev, B * V * max(C0, C1) * 4)
         ld2 = packed2.shape[1]
 
-        def wgrad(dyt, cout, xin, cin, g):
+        def wgrad(dyt, cout, xin, cin, g, dbias=None):
             gr = _zeros((cout, g.ntaps * cin), f32, dev)
-            _conv_call('wgrad', 2.0 * B * V * cout * cin * g.ntaps, 'og_conv3d_wgrad', dyt.data_ptr(), cout,
-                       xin.data_ptr(), cin, gr.data_ptr(), gr.shape[1], g.kt, g.kh, g.kw, g.pt, g.ph, g.pw, B, T, H, W, s)
+            if dbias is None:
+                _conv_call('wgrad', 2.0 * B * V * cout * cin * g.ntaps, 'og_conv3d_wgrad', dyt.data_ptr(), cout,
+                           xin.data_ptr(), cin, gr.data_ptr(), gr.shape[1], g.kt, g.kh, g.kw, g.pt, g.ph, g.pw, B, T, H, W, s)
+            else:       # + the bias gradient (column sums of dy) out of the same tensor-core pass
+                _conv_call('wgrad', 2.0 * B * V * cout * cin * g.ntaps, 'og_conv3d_wgrad_bias', dyt.data_ptr(), cout,
+                           xin.data_ptr(), cin, gr.data_ptr(), gr.shape[1], g.kt, g.kh, g.kw, g.pt, g.ph, g.pw, B, T, H, W,
+                           dbias.data_ptr(), cout, s)
             return gr.view(cout, g.kt, g.kh, g.kw, cin).permute(0, 4, 1, 2, 3)
 
         gone = ConvGeom(C0, C1, (1, 1, 1))
         db2 = _zeros(C1, f32, dev)
-        _lib.call('og_colsum', dyb.data_ptr(), B * V, C1, C1, db2.data_ptr(), s)
         dw2 = wgrad(dyb, C1, a2, C1, geom2)
-        dwres = wgrad(dyb, C1, xi, C0, gone)
+        dwres = wgrad(dyb, C1, xi, C0, gone, dbias=db2 if FUSE_BIAS_GRAD else None)   # 1 tap: spare accumulator columns
+        if not FUSE_BIAS_GRAD:
+            _lib.call('og_colsum', dyb.data_ptr(), B * V, C1, C1, db2.data_ptr(), s)
         # conv2 data gradient + fused GN2 backward reduction
         S2 = _zeros((B, C1, 2), f32, dev)
         d_a2 = empty_internal(B, C1, T, H, W, bf16, dev)

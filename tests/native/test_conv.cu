@@ -285,8 +285,21 @@ static bool run_case(const Case& c, bool do_dgrad, bool do_wgrad) {
       CK(cudaMalloc(&dw, nw * 4));
       CK(cudaMalloc(&dwr, nw * 4));
       CK(cudaMemset(dw, 0, nw * 4));
-      r = og_conv3d_wgrad(dy, c.cout, x0, c.c0, dw, (int64_t)ntaps * c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, c.N, c.T,
-                          c.H, c.W, 0);
+      // weight gradient + bias gradient (column sums of dy) in one launch; og_colsum is the reference for the latter
+      float *db, *dbr;
+      CK(cudaMalloc(&db, c.cout * 4));
+      CK(cudaMalloc(&dbr, c.cout * 4));
+      CK(cudaMemset(db, 0, c.cout * 4));
+      CK(cudaMemset(dbr, 0, c.cout * 4));
+      r = og_conv3d_wgrad_bias(dy, c.cout, x0, c.c0, dw, (int64_t)ntaps * c.c0, c.kt, c.kh, c.kw, c.pt, c.ph, c.pw, c.N, c.T,
+                               c.H, c.W, db, c.cout, 0);
+      if (r == 0) r = og_colsum(dy, V, c.cout, c.cout, dbr, 0);
+      if (r == 0) {
+        CK(cudaDeviceSynchronize());
+        ok &= compare("wgrad(bias gradient)", db, dbr, c.cout, 2e-3f, 5e-2f);
+      }
+      CK(cudaFree(db));
+      CK(cudaFree(dbr));
       if (r != 0) {
         printf("  og_conv3d_wgrad failed: %d %s\n", r, og_last_error());
         ok = false;
