@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from open_genie_b200 import _lib
-nseq, S, nh = int(os.environ.get('NSEQ', 32)), 4096, 4
+nseq, S, nh = int(os.environ.get('NSEQ', 32)), int(os.environ.get('SEQ', 4096)), 4
 C = nh * 64
 s = torch.cuda.current_stream().cuda_stream
 q, k, v, do = (torch.randn(nseq, S, C, device='cuda').mul_(0.5).bfloat16() for _ in range(4))
