@@ -14,6 +14,8 @@
 // Q/K/V tiles arrive by 3-D TMA (rows beyond S are zero-filled and masked to -inf).
 // Backward recomputes P from the saved log-sum-exp and accumulates dK/dV in TMEM per key tile, dQ via
 // fp32 reductions (see og_flash_attn_bwd_kernel).
+#include <type_traits>
+
 #include "og_host.cuh"
 #include "og_ptx.cuh"
 
@@ -1049,6 +1051,381 @@ __global__ void __launch_bounds__(64 + 32 * NW, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, persistent form of og_flash_attn_bwd2_kernel (8 softmax warps): one CTA per SM walks the work items
+// (frame, head, own tile) w = blockIdx.x, blockIdx.x + gridDim.x, ... with the same pipeline, but TMEM, the barriers and
+// the tensor maps are set up ONCE, and the next item's stationary / first streamed tiles are loaded (and its S(0), dP(0)
+// issued) while the softmax warps still store the current item's accumulators. All barrier parities derive from running
+// counters: T = global index of the streamed tile (slot T % kStages, S buffer T & 1), wi = index of the work item.
+// Measured motivation (profiles/r02u_ncu_flash_attention_bwd.md): ~6 us of fixed cost per CTA, 12 % of the backward at
+// S = 4096 and 75 % at S = 256.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kFaBwdThreads, 1)
+    og_flash_attn_bwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                              const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
+                              const FaBwdParams p, const int total_items) {
+  constexpr int kStages = MODE == 0 ? 2 : 4;   // power of two
+  constexpr int NW = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sFix = smem;                    // stationary pair: MODE 0: K_j, V_j ; MODE 1: Q_i, dO_i   (2 x 16 KiB)
+  uint8_t* sStr = smem + 2 * kTileBytes;   // streamed pair, kStages x (2 x 16 KiB)   (MODE 1: covers the unused P region)
+  uint8_t* sP = smem + 6 * kTileBytes;     // P  bf16 [2 buffers][2 k-blocks][128][128 B]   (MODE 0 only)
+  uint8_t* sDS = smem + 10 * kTileBytes;   // dS bf16, same shape
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 14 * kTileBytes);
+  uint64_t* fix_full = bars;
+  uint64_t* fix_empty = bars + 1;
+  uint64_t* str_full = bars + 2;   // [4]
+  uint64_t* str_empty = bars + 6;  // [4]
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* dp_full = bars + 12;
+  uint64_t* dp_free = bars + 13;
+  uint64_t* p_ready = bars + 14;
+  uint64_t* acc_ready = bars + 15;
+  uint64_t* acc_free = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    tma_prefetch_desc(&mapDO);
+    mbar_init(fix_full, 1);
+    mbar_init(fix_empty, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&str_full[s], 1);
+      mbar_init(&str_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(dp_full, 1);
+    mbar_init(dp_free, NW);
+    mbar_init(p_ready, NW);
+    mbar_init(acc_ready, 1);
+    mbar_init(acc_free, NW);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS0 = tmem_base, tDP = tmem_base + 256, tAcc0 = tmem_base + 384, tAcc1 = tmem_base + 448;
+  const int tiles = p.tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    int T = 0, wi = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++wi) {
+      int id = w;
+      const int own = id % tiles;
+      id /= tiles;
+      const int h = id % p.nh, seq = id / p.nh;
+      mbar_wait(fix_empty, (wi & 1) ^ 1);   // the previous item's last S / dP MMAs have read the stationary tiles
+      if (elect_one()) {
+        mbar_expect_tx(fix_full, 2 * kTileBytes);
+        if (MODE == 0) {
+          tma_load_3d(sFix, &mapK, fix_full, h * kD, own * kTile, seq);
+          tma_load_3d(sFix + kTileBytes, &mapV, fix_full, h * kD, own * kTile, seq);
+        } else {
+          tma_load_3d(sFix, &mapQ, fix_full, h * kD, own * kTile, seq);
+          tma_load_3d(sFix + kTileBytes, &mapDO, fix_full, h * kD, own * kTile, seq);
+        }
+      }
+      __syncwarp();
+      for (int it = 0; it < tiles; ++it, ++T) {
+        const int st = T & (kStages - 1);
+        mbar_wait(&str_empty[st], ((T / kStages) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&str_full[st], 2 * kTileBytes);
+          uint8_t* d = sStr + st * 2 * kTileBytes;
+          if (MODE == 0) {
+            tma_load_3d(d, &mapQ, &str_full[st], h * kD, it * kTile, seq);
+            tma_load_3d(d + kTileBytes, &mapDO, &str_full[st], h * kD, it * kTile, seq);
+          } else {
+            tma_load_3d(d, &mapK, &str_full[st], h * kD, it * kTile, seq);
+            tma_load_3d(d + kTileBytes, &mapV, &str_full[st], h * kD, it * kTile, seq);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    const uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0u, 0u);  // S, dP: both operands K-major
+    const uint32_t idesc_mm = umma_idesc_bf16(128, 64, 1u, 1u);   // dV, dK: A (P / dS transposed) and B MN-major
+    const uint32_t idesc_km = umma_idesc_bf16(128, 64, 0u, 1u);   // dQ: A = dS K-major, B = K MN-major
+    const uint32_t p_base = smem_u32(sP), ds_base = smem_u32(sDS);
+    const uint32_t fixa = smem_u32(sFix), str0 = smem_u32(sStr);
+    int T0 = 0, wi = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++wi, T0 += tiles) {
+      mbar_wait(fix_full, wi & 1);
+      tc_fence_after();
+      {  // S(0) of this item
+        const int st = T0 & (kStages - 1);
+        mbar_wait(&str_full[st], (T0 / kStages) & 1);
+        tc_fence_after();
+        const uint32_t stra = str0 + st * 2 * kTileBytes;
+        const uint32_t q_addr = MODE == 0 ? stra : fixa, k_addr = MODE == 0 ? fixa : stra;
+        const uint32_t tS = tS0 + ((T0 & 1) ? 128u : 0u);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k)
+            umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[T0 & 1]);
+        }
+        __syncwarp();
+      }
+      for (int it = 0; it <= tiles; ++it) {
+        const int T = T0 + it;
+        if (it < tiles) {  // dP(it)
+          if (T > 0) {
+            mbar_wait(dp_free, (T - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t stra = str0 + (T & (kStages - 1)) * 2 * kTileBytes;
+          const uint32_t do_addr = (MODE == 0 ? stra : fixa) + kTileBytes, v_addr = (MODE == 0 ? fixa : stra) + kTileBytes;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k)
+              umma_bf16_ss(tDP, umma_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                           umma_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+            umma_commit(dp_full);
+            if (it == tiles - 1) umma_commit(fix_empty);   // every S / dP of this item has been issued
+          }
+          __syncwarp();
+        }
+        if (it > 0) {  // gradient MMAs of tile it-1
+          const int jj = it - 1, Tj = T - 1;
+          mbar_wait(p_ready, Tj & 1);
+          tc_fence_after();
+          if (jj == 0 && wi > 0) {   // they overwrite the accumulators: the previous item's must be in registers
+            mbar_wait(acc_free, (wi - 1) & 1);
+            tc_fence_after();
+          }
+          const int st = Tj & (kStages - 1);
+          const uint32_t stra = str0 + st * 2 * kTileBytes;
+          const uint32_t p_addr = p_base + (Tj & 1) * 2 * kTileBytes, ds_addr = ds_base + (Tj & 1) * 2 * kTileBytes;
+          if (!elect_one()) {
+          } else if (MODE == 0) {
+            const uint32_t q_addr = stra, do_addr = stra + kTileBytes;
+#pragma unroll
+            for (int k = 0; k < kTile / 16; ++k) {  // K dim = 128 query rows, 16 per MMA
+              umma_bf16_ss(tAcc0, umma_smem_desc_sw128(p_addr + k * 2048, kTileBytes, 1024),
+                           umma_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), idesc_mm, (jj > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_ss(tAcc1, umma_smem_desc_sw128(ds_addr + k * 2048, kTileBytes, 1024),
+                           umma_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), idesc_mm, (jj > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+            const uint32_t k_addr = stra;
+#pragma unroll
+            for (int k = 0; k < kTile / 16; ++k)  // K dim = 128 keys
+              umma_bf16_ss(tAcc0, umma_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                           umma_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), idesc_km, (jj > 0 || k > 0) ? 1u : 0u);
+          }
+          __syncwarp();
+          if (elect_one()) umma_commit(&str_empty[st]);
+          __syncwarp();
+        }
+        if (it + 1 < tiles) {  // S(it+1)
+          const int Tn = T + 1, st = Tn & (kStages - 1);
+          mbar_wait(&str_full[st], (Tn / kStages) & 1);
+          tc_fence_after();
+          const uint32_t stra = str0 + st * 2 * kTileBytes;
+          const uint32_t q_addr = MODE == 0 ? stra : fixa, k_addr = MODE == 0 ? fixa : stra;
+          const uint32_t tS = tS0 + ((Tn & 1) ? 128u : 0u);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k)
+              umma_bf16_ss(tS, umma_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           umma_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_kk, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[Tn & 1]);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) umma_commit(acc_ready);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ softmax / epilogue warps
+    const int qd = warp & 3;
+    const int cg = (warp - 2) >> 2;      // column group: 64 of the 128 columns of S / dP
+    const int c0 = cg * 64;
+    const int row = qd * 32 + lane;      // TMEM lane: query row of the current pair
+    const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+    const float cl2 = p.scale * 1.4426950408889634f;
+    int T0 = 0, wi = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++wi, T0 += tiles) {
+      int id = w;
+      const int own = id % tiles;
+      id /= tiles;
+      const int h = id % p.nh, seq = id / p.nh;
+      const float* lse_row = p.lse + ((long long)seq * p.nh + h) * p.S;
+      const float* delta_row = p.delta + ((long long)seq * p.nh + h) * p.S;
+      float lse_fix = 0.f, delta_fix = 0.f, lse_nxt = 0.f, delta_nxt = 0.f;
+      if (MODE == 1) {
+        const int qrow = own * kTile + row;
+        if (qrow < p.S) {
+          lse_fix = __ldg(lse_row + qrow) * 1.4426950408889634f;
+          delta_fix = __ldg(delta_row + qrow);
+        }
+      } else if (row < p.S) {
+        lse_nxt = __ldg(lse_row + row);
+        delta_nxt = __ldg(delta_row + row);
+      }
+      for (int it = 0; it < tiles; ++it) {
+        const int T = T0 + it;
+        const int q_tile = MODE == 0 ? it : own, kv_tile = MODE == 0 ? own : it;
+        const int qrow = q_tile * kTile + row;
+        float lse2 = lse_fix, delta = delta_fix;
+        if (MODE == 0) {
+          lse2 = lse_nxt * 1.4426950408889634f;
+          delta = delta_nxt;
+          if (qrow + kTile < p.S) {
+            lse_nxt = __ldg(lse_row + qrow + kTile);
+            delta_nxt = __ldg(delta_row + qrow + kTile);
+          }
+        }
+        const bool q_ok = qrow < p.S;
+        const int kv_valid = p.S - kv_tile * kTile;
+        const bool full = (q_tile + 1) * kTile <= p.S && kv_valid >= kTile;  // warp-uniform fast path
+        const uint32_t tS = tS0 + ((T & 1) ? 128u : 0u);
+        uint8_t* sPb = sP + (T & 1) * 2 * kTileBytes;
+        uint8_t* sDSb = sDS + (T & 1) * 2 * kTileBytes;
+        float pf[64];
+        uint32_t vs[32], vd[32];
+        mbar_wait(&s_full[T & 1], (T >> 1) & 1);
+        tc_fence_after();
+        // chunk 0 exponentials
+        tmem_ld_32x32(tS + lane_addr + c0, vs);
+        tmem_ld_wait();
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pf[i] = ex2_approx(fmaf(__uint_as_float(vs[i]), cl2, -lse2));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float pv = ex2_approx(fmaf(__uint_as_float(vs[i]), cl2, -lse2));
+            pf[i] = (q_ok && (c0 + i < kv_valid)) ? pv : 0.f;
+          }
+        }
+        mbar_wait(dp_full, T & 1);
+        tc_fence_after();
+        tmem_ld_32x32(tDP + lane_addr + c0, vd);
+        tmem_ld_32x32(tS + lane_addr + c0 + 32, vs);
+        tmem_ld_wait();
+        // chunk 1 exponentials interleaved with chunk 0's P / dS work (two copies: the whole-tile one carries no
+        // per-element compare / select)
+        auto chunk1 = [&](auto whole) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float pv = ex2_ordered(fmaf(__uint_as_float(vs[i + e]), cl2, -lse2));
+            if constexpr (decltype(whole)::value)
+              pf[32 + i + e] = pv;
+            else
+              pf[32 + i + e] = (q_ok && (c0 + 32 + i + e < kv_valid)) ? pv : 0.f;
+          }
+          const int col = c0 + i;
+          uint4 u;
+          if (MODE == 0) {
+            u.x = pack_bf16x2(pf[i], pf[i + 1]);
+            u.y = pack_bf16x2(pf[i + 2], pf[i + 3]);
+            u.z = pack_bf16x2(pf[i + 4], pf[i + 5]);
+            u.w = pack_bf16x2(pf[i + 6], pf[i + 7]);
+            st_swizzled_chunk_ordered(sPb + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+          }
+          float df[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) df[e] = pf[i + e] * (__uint_as_float(vd[i + e]) - delta);
+          u.x = pack_bf16x2(df[0], df[1]);
+          u.y = pack_bf16x2(df[2], df[3]);
+          u.z = pack_bf16x2(df[4], df[5]);
+          u.w = pack_bf16x2(df[6], df[7]);
+          st_swizzled_chunk_ordered(sDSb + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+        }
+        };
+        if (full)
+          chunk1(std::true_type{});
+        else
+          chunk1(std::false_type{});
+        tmem_ld_32x32(tDP + lane_addr + c0 + 32, vd);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_free);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const int col = c0 + 32 + i;
+          uint4 u;
+          if (MODE == 0) {
+            u.x = pack_bf16x2(pf[32 + i], pf[32 + i + 1]);
+            u.y = pack_bf16x2(pf[32 + i + 2], pf[32 + i + 3]);
+            u.z = pack_bf16x2(pf[32 + i + 4], pf[32 + i + 5]);
+            u.w = pack_bf16x2(pf[32 + i + 6], pf[32 + i + 7]);
+            st_swizzled_chunk(sPb + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+          }
+          float df[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) df[e] = pf[32 + i + e] * (__uint_as_float(vd[i + e]) - delta);
+          u.x = pack_bf16x2(df[0], df[1]);
+          u.y = pack_bf16x2(df[2], df[3]);
+          u.z = pack_bf16x2(df[4], df[5]);
+          u.w = pack_bf16x2(df[6], df[7]);
+          st_swizzled_chunk(sDSb + (col >> 6) * kTileBytes, row, (col & 63) >> 3, u);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+      }
+      // accumulators of this item: TMEM -> registers, hand TMEM back, then scale / round / store
+      mbar_wait_relaxed(acc_ready, wi & 1);
+      tc_fence_after();
+      uint32_t va[2][32];
+      tmem_ld_32x32(tAcc0 + lane_addr + cg * 32, va[0]);
+      if (MODE == 0) tmem_ld_32x32(tAcc1 + lane_addr + cg * 32, va[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+      const int orow = own * kTile + row;
+      if (orow < p.S) {
+#pragma unroll
+        for (int a = 0; a < (MODE == 0 ? 2 : 1); ++a) {
+          __nv_bfloat16* base = MODE == 1 ? p.dq : (a == 0 ? p.dv : p.dk);
+          const float osc = (MODE == 0 && a == 0) ? 1.f : p.scale;
+          __nv_bfloat16* dst = base + ((long long)seq * p.S + orow) * p.C + h * kD + cg * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(va[a][i]) * osc, __uint_as_float(va[a][i + 1]) * osc);
+            u.y = pack_bf16x2(__uint_as_float(va[a][i + 2]) * osc, __uint_as_float(va[a][i + 3]) * osc);
+            u.z = pack_bf16x2(__uint_as_float(va[a][i + 4]) * osc, __uint_as_float(va[a][i + 5]) * osc);
+            u.w = pack_bf16x2(__uint_as_float(va[a][i + 6]) * osc, __uint_as_float(va[a][i + 7]) * osc);
+            *reinterpret_cast<uint4*>(dst + i) = u;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // delta[seq][h][s] = sum_d dO * O   (one warp per row, lanes over the head's 64 dims)
 __global__ void og_attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                      float* __restrict__ delta, long long rows, int S, int C, int nh) {
@@ -1151,7 +1528,8 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
     OG_CHECK_CUDA(cudaFuncSetAttribute(og_flash_attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_bytes));
     const void* k2[] = {(const void*)og_flash_attn_bwd2_kernel<0, 8>, (const void*)og_flash_attn_bwd2_kernel<1, 8>,
-                        (const void*)og_flash_attn_bwd2_kernel<0, 16>, (const void*)og_flash_attn_bwd2_kernel<1, 16>};
+                        (const void*)og_flash_attn_bwd2_kernel<0, 16>, (const void*)og_flash_attn_bwd2_kernel<1, 16>,
+                        (const void*)og_flash_attn_bwd3_kernel<0>, (const void*)og_flash_attn_bwd3_kernel<1>};
     for (const void* f : k2)
       OG_CHECK_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr = true;
@@ -1182,7 +1560,16 @@ extern "C" int og_flash_attn_bwd(const void* q, const void* k, const void* v, co
       const char* e = getenv("OG_FLASH_BWD_WARPS");   // 8 or 16 softmax warps
       return (e && atoi(e) == 16) ? 16 : 8;
     }();
-    if (nw == 8) {
+    static const int persistent = [] {
+      const char* e = getenv("OG_FLASH_BWD_PERSISTENT");   // 0: one CTA per work item (og_flash_attn_bwd2_kernel)
+      return (e && atoi(e) == 0) ? 0 : 1;
+    }();
+    if (persistent && nw == 8 && p.interleave && !p.dbg && grid < (1LL << 31)) {
+      const int items = (int)grid;
+      const int ctas = items < num_sms() ? items : num_sms();
+      og_flash_attn_bwd3_kernel<0><<<ctas, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p, items);
+      og_flash_attn_bwd3_kernel<1><<<ctas, kFaBwdThreads, smem_bytes, s>>>(mq, mk, mv, mdo, p, items);
+    } else if (nw == 8) {
       og_flash_attn_bwd2_kernel<0, 8><<<(unsigned)grid, 64 + 32 * 8, smem_bytes, s>>>(mq, mk, mv, mdo, p);
       og_flash_attn_bwd2_kernel<1, 8><<<(unsigned)grid, 64 + 32 * 8, smem_bytes, s>>>(mq, mk, mv, mdo, p);
     } else {

@@ -1,7 +1,7 @@
 """The opt-in kernel paths read their switches once per process, so they are exercised by re-running the relevant parity
 tests in a child process with the switch set: conv3d split-K variants (in-kernel finish, round-1 atomic form) and the
 dynamic tile scheduler against the convolution / tokenizer tests; the flash-attention backward variants (first
-un-pipelined version, 16 softmax warps, no exp / dS interleave) against the attention tests."""
+un-pipelined version, 16 softmax warps, no exp / dS interleave, one CTA per work item) against the attention tests."""
 import os
 import subprocess
 import sys
@@ -28,6 +28,7 @@ def test_conv_parity_with_optin_switch(switch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('switch', ['OG_FLASH_BWD_V1=1', 'OG_FLASH_BWD_WARPS=16', 'OG_FLASH_BWD_INTERLEAVE=0'])
+@pytest.mark.parametrize('switch', ['OG_FLASH_BWD_V1=1', 'OG_FLASH_BWD_WARPS=16', 'OG_FLASH_BWD_INTERLEAVE=0',
+                                    'OG_FLASH_BWD_PERSISTENT=0'])
 def test_attention_parity_with_optin_switch(switch):
     _rerun(ATTN_TESTS, switch)
