@@ -29,6 +29,6 @@ def test_conv_parity_with_optin_switch(switch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('switch', ['OG_FLASH_BWD_V1=1', 'OG_FLASH_BWD_WARPS=16', 'OG_FLASH_BWD_INTERLEAVE=0',
-                                    'OG_FLASH_BWD_PERSISTENT=0'])
+                                    'OG_FLASH_BWD_PERSISTENT=0', 'OG_FLASH_FWD_PERSISTENT=2', 'OG_FLASH_FWD_PERSISTENT=0'])
 def test_attention_parity_with_optin_switch(switch):
     _rerun(ATTN_TESTS, switch)
