@@ -1796,13 +1796,13 @@ extern "C" int og_flash_attn_fwd(const void* q, const void* k, const void* v, vo
   const long long grid = (long long)nseq * n_head * p.q_tiles;
   // Persistent form for SHORT sequences only. Measured on B200 (32 x 4096 / 128 x 1024 / 512 x 256 tokens, 4 heads):
   // 0.888 vs 0.857 ms at S = 4096 (static round-robin of 4096 equal items loses to the hardware's dynamic CTA placement with two
-  // CTAs per SM), 0.251 vs 0.254 at S = 1024, 0.086 vs 0.106 at S = 256 (where the per-CTA set-up is half of the kernel).
-  // OG_FLASH_FWD_PERSISTENT: 0 = never, 2 = always, otherwise S <= 512.
+  // CTAs per SM), 0.251 vs 0.254 at S = 1024, 0.196 vs 0.204 at S = 768, 0.141 vs 0.157 at S = 512, 0.086 vs 0.106 at S = 256
+  // (where the per-CTA set-up is half of the kernel). OG_FLASH_FWD_PERSISTENT: 0 = never, 2 = always, otherwise S <= 1024.
   static const int persistent = [] {
     const char* e = getenv("OG_FLASH_FWD_PERSISTENT");
     return e ? atoi(e) : 1;
   }();
-  if ((persistent == 2 || (persistent == 1 && p.kv_tiles <= 4)) && grid < (1LL << 31)) {
+  if ((persistent == 2 || (persistent == 1 && p.kv_tiles <= 8)) && grid < (1LL << 31)) {
     const int items = (int)grid;
     const int ctas = items < 2 * num_sms() ? items : 2 * num_sms();
     og_flash_attn_fwd2_kernel<<<ctas, kFaThreads, smem_bytes, (cudaStream_t)stream>>>(mq, mk, mv, p, items);
