@@ -12,8 +12,16 @@
 //   PV = P V             tcgen05.mma, A = P (K-major, smem), B = V tile (MN-major: keys are the K dim)
 //   O += PV              accumulated in TMEM by the MMA; rescaled in place only when a row maximum jumps (lazy rescale)
 // Q/K/V tiles arrive by 3-D TMA (rows beyond S are zero-filled and masked to -inf).
-// Backward recomputes P from the saved log-sum-exp and accumulates dK/dV in TMEM per key tile, dQ via
-// fp32 reductions (see og_flash_attn_bwd_kernel).
+// Backward recomputes P from the saved log-sum-exp in two passes: dV / dK accumulate in TMEM per key tile, dQ per query
+// tile (no atomics, no fp32 gradient buffers).
+//
+// Kernels in this file (the host entry points pick; DESIGN.md section 6 has the measurements behind each step):
+//   og_flash_attn_fwd_kernel    one CTA per work item, two CTAs per SM                          (S > 1024)
+//   og_flash_attn_fwd2_kernel   persistent form of it                                           (S <= 1024)
+//   og_flash_attn_bwd3_kernel   backward, software-pipelined AND persistent                     (default)
+//   og_flash_attn_bwd2_kernel   backward, software-pipelined, one CTA per work item             (OG_FLASH_BWD_PERSISTENT=0,
+//                               16-warp / non-interleaved variants, knock-out timing switches)
+//   og_flash_attn_bwd_kernel    backward, first version: S,dP -> softmax -> gradients in turn   (OG_FLASH_BWD_V1=1)
 #include <type_traits>
 
 #include "og_host.cuh"
