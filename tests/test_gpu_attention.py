@@ -98,6 +98,32 @@ def test_flash_attention_fwd_bwd(S, nh, amp):
         assert rel_l2(got.float().cpu(), ref) < 2e-2, (name, rel_l2(got.float().cpu(), ref))
 
 
+# Many more work items than SMs with ODD tile counts per item (1, 3, 5): every persistent CTA walks several items, so the
+# running-counter barrier parities of og_flash_attn_fwd2 / bwd3 cross item boundaries on both phases of every barrier.
+# Reference: torch's SDPA in fp32 on the GPU (the small cases above pin the kernels to the CPU oracle values).
+@pytest.mark.parametrize('S,nseq,nh', [(64, 200, 2), (320, 120, 1), (640, 40, 2)])
+def test_flash_attention_many_items_per_cta(S, nseq, nh):
+    C = 64 * nh
+    scale = nh * 64 ** -0.5
+    g = torch.Generator(device='cpu').manual_seed(S)
+    q, k, v, do = (torch.randn(nseq, S, C, generator=g).mul_(0.5).to(DEV).to(torch.bfloat16) for _ in range(4))
+    sp = lambda t: t.float().reshape(nseq, S, nh, 64).transpose(1, 2)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    oo = F.scaled_dot_product_attention(sp(qr), sp(kr), sp(vr), scale=scale).transpose(1, 2).reshape(nseq, S, C)
+    oo.backward(do.float())
+    out = torch.empty_like(q)
+    lse = torch.empty((nseq, nh, S), device=DEV)
+    _call('og_flash_attn_fwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), None, None, lse.data_ptr(),
+          nseq, S, C, nh, scale)
+    assert rel_l2(out.float().cpu(), oo.detach().cpu()) < 1e-2
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    delta = torch.empty_like(lse)
+    _call('og_flash_attn_bwd', q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(),
+          delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), nseq, S, C, nh, scale)
+    for name, got, ref in (('dq', dq, qr.grad), ('dk', dk, kr.grad), ('dv', dv, vr.grad)):
+        assert rel_l2(got.float().cpu(), ref.float().cpu()) < 2e-2, (name, rel_l2(got.float().cpu(), ref.float().cpu()))
+
+
 @pytest.mark.parametrize('bcast', [False, True])
 def test_temporal_attention_fwd_bwd(bcast):
     B, T, P, nh = 2, 8, 24, 2
